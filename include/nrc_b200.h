@@ -1,0 +1,129 @@
+/*
+ * nrc_b200.h -- C ABI of the B200-native Neural-Radiance-Cache MLP (drop-in for VkNRC's hot path).
+ *
+ * The reference has no FFI boundary for this path: the MLP sits behind (i) the `VkNRCState` object
+ * (src/VkNRCState.hpp:17-90) plus the descriptor-binding tables of its render-graph passes
+ * (src/rg/NNInference.cpp:13-48, src/rg/NNTrain.cpp:59-66, 91-104) and (ii) the vuda `launchKernel` calls of the
+ * test harness (test/main.cpp:116-117, 180-181). Each entry point below names the reference interface it replaces.
+ *
+ * Conventions: every function returns 0 on success and a negative NRC_ERR_* otherwise (never throws, never aborts);
+ * nrc_last_error() returns a thread-local description of the last failure. All `d_*` pointers are CUDA device
+ * pointers on the handle's device; `stream` is a cudaStream_t passed as void*. Work is enqueued, not synchronised,
+ * and counts are read on the device (the reference uses indirect dispatch, src/rg/NNDispatch.hpp:22-44), so a frame
+ * never needs a host round trip. A handle is not thread-safe (the reference records one command buffer per frame
+ * on one thread, src/main.cpp:160-169).
+ *
+ * Buffer layouts are bit-identical to the reference's (see vknrc_b200/csrc/nrc_config.h):
+ *   weights / use_weights  fp16 row-major W[l][out][in], layer l at l*4096, layer 5 = 3x64 at 20480 (NN_nv.glsl:69-82)
+ *   optimizer_entries      {m, v, weight, ema_weight} fp32 (src/VkNRCState.cpp:29-31)
+ *   optimizer_state        {u32 t; f32 beta1_t, beta2_t, alpha_t, alpha_t_1}   (src/VkNRCState.cpp:25-28)
+ *   eval / train records   NRCEvalRecord 20 B, NRCTrainRecord 40 B             (shader/src/NRCRecord.glsl:6-38)
+ *   gradients              fp32, weight layout, + [20672] loss sum, [20673] record count, padded to 20736
+ */
+#ifndef NRC_B200_H
+#define NRC_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NRC_OK 0
+#define NRC_ERR_INVALID_ARGUMENT (-1)
+#define NRC_ERR_CUDA (-2)
+#define NRC_ERR_UNSUPPORTED_DEVICE (-3) /* not an sm_100 part: there is no fallback path */
+#define NRC_ERR_OUT_OF_MEMORY (-4)
+
+#define NRC_B200_WEIGHT_COUNT 20672u
+#define NRC_B200_GRADIENT_FLOATS 20736u
+#define NRC_B200_GRAD_LOSS_SLOT 20672u
+#define NRC_B200_GRAD_COUNT_SLOT 20673u
+
+typedef struct nrc_state_t *nrc_handle_t;
+
+typedef struct nrc_config_t {
+	uint32_t extent_width, extent_height; /* VkNRCState(queue, extent), src/VkNRCState.hpp:37 */
+	uint64_t seed;                        /* explicit: the reference seeds from std::random_device */
+} nrc_config_t;
+
+const char *nrc_last_error(void);
+
+/* ---- VkNRCState statics (src/VkNRCState.hpp:83-89, src/VkNRCState.cpp:34-37) ---- */
+uint64_t nrc_get_eval_record_buffer_size(uint32_t extent_width, uint32_t extent_height);
+uint64_t nrc_get_batch_train_record_buffer_size(void);
+uint32_t nrc_get_train_batch_count(void);
+uint32_t nrc_get_train_batch_size(void);
+uint32_t nrc_get_weight_count(void);
+float nrc_get_default_train_probability(void);
+
+/* ---- VkNRCState object (src/VkNRCState.hpp:37-81) ---- */
+int nrc_create(const nrc_config_t *config, int device, nrc_handle_t *out);                 /* ctor, :37-40 */
+void nrc_destroy(nrc_handle_t h);
+int nrc_reset_mlp_buffers(nrc_handle_t h, uint64_t seed);  /* ResetMLPBuffers, src/VkNRCState.cpp:46-88 (He-normal) */
+int nrc_set_weights(nrc_handle_t h, const float *host_fp32_weights); /* same upload path, caller-provided values */
+void *nrc_get_weight_buffer(nrc_handle_t h);               /* GetWeightBuffer,          fp16 x 20672 (device) */
+void *nrc_get_use_weight_buffer(nrc_handle_t h);           /* GetUseWeightBuffer,       fp16 x 20672 (device) */
+void *nrc_get_optimizer_entry_buffer(nrc_handle_t h);      /* GetOptimizerEntryBuffer,  16 B x 20672 (device) */
+void *nrc_get_optimizer_state_buffer(nrc_handle_t h);      /* GetOptimizerStateBuffer,  20 B (device) */
+void *nrc_get_gradient_buffer(nrc_handle_t h);             /* `gradients` of NNTrain (src/rg/NNTrain.hpp:96-98): fp32 x 20736 */
+int nrc_download(nrc_handle_t h, uint16_t *weights, uint16_t *use_weights, void *optimizer_entries,
+                 void *optimizer_state, float *gradients, void *stream); /* any pointer may be NULL; synchronises */
+void nrc_set_use_ema_weights(nrc_handle_t h, int use_ema); /* SetUseEMAWeights */
+int nrc_is_use_ema_weights(nrc_handle_t h);
+void nrc_set_train_probability(nrc_handle_t h, float p);   /* SetTrainProbability (consumed by the record producer) */
+float nrc_get_train_probability(nrc_handle_t h);
+uint32_t nrc_next_frame(nrc_handle_t h);                   /* NextFrame: advances and returns the per-frame seed */
+uint32_t nrc_get_seed(nrc_handle_t h);
+
+/* ---- test-harness kernels on pre-encoded inputs ----
+ * nrc_mlp_evaluate_encoded == launchKernel("evaluate_32.spv", ..., weights, inputs, outputs)   (test/main.cpp:116-117)
+ * nrc_mlp_gradient_encoded == launchKernel("train_32.spv", ..., weights, dw, inputs, targets)  (test/main.cpp:180-181)
+ * inputs [n][64] fp16, outputs/targets [n][3] fp16, dw fp32 x 20672 ACCUMULATED into (L2 loss, test/train_NV.comp).
+ * n need not be a multiple of 128 (the reference's test kernels require it). */
+int nrc_mlp_evaluate_encoded(const void *d_weights, const void *d_inputs, void *d_outputs, uint64_t n, void *stream);
+int nrc_mlp_gradient_encoded(const void *d_weights, float *d_dw, const void *d_inputs, const void *d_targets,
+                             uint64_t n, void *stream);
+
+/* ---- inference (nrc_inference.comp; bindings src/rg/NNInference.cpp:13-48), weights = use_weights ----
+ * `d_count` may be NULL (then max_count queries run). */
+int nrc_infer_encoded(nrc_handle_t h, const void *d_inputs, void *d_outputs_f16vec3, uint64_t n, int clamp_output,
+                      void *stream);
+/* records = 14 fp32 each (UnpackedNRCInput order, NRCRecord.glsl:40-45) `stride_bytes` apart; outputs max(y,0) fp16x3 */
+int nrc_infer_unpacked(nrc_handle_t h, const void *d_records, uint32_t stride_bytes, const uint32_t *d_count,
+                       uint64_t max_count, void *d_outputs_f16vec3, void *stream);
+/* full output stage of nrc_inference.comp:48-73: dst words (NRCRecord.glsl:19-33) `dst_stride_bytes` apart select
+ * screen (bias_factor_r rgba32f RMW + factor_gb rg32f, `image_pitch` pixels per row) or train-record feedback. */
+int nrc_infer_scatter_unpacked(nrc_handle_t h, const uint32_t *d_dst, uint32_t dst_stride_bytes, const void *d_records,
+                               uint32_t stride_bytes, const uint32_t *d_count, uint64_t max_count, void *d_bias_factor_r,
+                               const void *d_factor_gb, uint32_t image_pitch, void *const d_train_records[4], void *stream);
+
+/* ---- training (NNTrain pass group: clear -> prepare -> gradient -> optimize, src/rg/NNTrain.hpp:95-127) ----
+ * nrc_gradient_unpacked: gradient pass + deterministic batch reduction into the gradient buffer (replaces clear +
+ *   nrc_gradient.comp's atomics). inputs as above; targets = 3 fp32 (`bias`, NRCRecord.glsl:36) `target_stride` apart.
+ *   `d_count` (optional) is clamped in place to max_count like nrc_train_prepare.comp:17-19.
+ * nrc_adam_step: nrc_train_prepare.comp:22-28 + nrc_optimize.comp:32-54 using gradient[20673] as the record count
+ *   (so that a multi-GPU caller can all-reduce the gradient buffer in between); writes `weights`, and `use_weights`
+ *   iff write_use_weights (the reference does that for the frame's last batch only, NRCRenderGraph.cpp:66-68).
+ * nrc_train_batch_unpacked = both, back to back. */
+int nrc_gradient_unpacked(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets,
+                          uint32_t target_stride, uint32_t *d_count, uint32_t max_count, void *stream);
+int nrc_gradient_encoded(nrc_handle_t h, const void *d_inputs, const void *d_targets_f16vec3, uint32_t *d_count,
+                         uint32_t max_count, int relative_loss, void *stream);
+int nrc_adam_step(nrc_handle_t h, int write_use_weights, void *stream);
+int nrc_train_batch_unpacked(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets,
+                             uint32_t target_stride, uint32_t *d_count, uint32_t max_count, int write_use_weights,
+                             void *stream);
+/* optional fp32 [max_count][3] buffer that receives the (unclamped) training predictions of the next gradient call */
+void nrc_set_prediction_capture(nrc_handle_t h, float *d_predictions);
+
+/* ---- learn-an-image harness (test/mlp_learning_an_image/{gradient,optimize,inference}.comp) ----
+ * one training step: `batch` random uv samples (pcg2d stream of push-constant seeds), one-blob-32 encoding,
+ * bilinear RGBA8 target, L2 loss, SGD lr on the fp32 master weights; inference over a width x width grid to RGBA8. */
+int nrc_image_train_step(nrc_handle_t h, const void *d_image_rgba8, uint32_t image_w, uint32_t image_h, uint32_t seed_x,
+                         uint32_t seed_y, uint32_t batch, float lr, void *stream);
+int nrc_image_infer(nrc_handle_t h, void *d_out_rgba8, uint32_t width, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NRC_B200_H */

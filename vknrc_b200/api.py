@@ -1,0 +1,283 @@
+"""ctypes binding of ``libnrc_b200.so`` (the C ABI in ``include/nrc_b200.h``) for tests, bench and examples.
+
+This is plumbing, not the product: the product is the CUDA/C++ library. PyTorch is used only to own device memory,
+streams and (for multi-GPU) ``torch.distributed``. There is NO fallback: if the library is missing or the device is
+not an sm_100 part, every call fails loudly.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libnrc_b200.so")
+
+WEIGHT_COUNT = 20672
+GRADIENT_FLOATS = 20736
+GRAD_LOSS_SLOT = 20672
+GRAD_COUNT_SLOT = 20673
+TRAIN_BATCH_SIZE = 16384
+TRAIN_BATCH_COUNT = 4
+
+OPT_ENTRY_DTYPE = np.dtype([("m", "<f4"), ("v", "<f4"), ("weight", "<f4"), ("ema_weight", "<f4")])
+OPT_STATE_DTYPE = np.dtype([("t", "<u4"), ("beta1_t", "<f4"), ("beta2_t", "<f4"), ("alpha_t", "<f4"), ("alpha_t_1", "<f4")])
+# shader/src/NRCRecord.glsl:6-38
+PACKED_INPUT_DTYPE = np.dtype([("primitive_id", "<u4"), ("flip_bit_instance_id", "<u4"), ("barycentric_2x16U", "<u4"),
+                               ("scattered_dir_2x16U", "<u4")])
+EVAL_RECORD_DTYPE = np.dtype([("dst", "<u4"), ("packed_input", PACKED_INPUT_DTYPE)])
+TRAIN_RECORD_DTYPE = np.dtype([("bias", "<f4", 3), ("factor", "<f4", 3), ("packed_input", PACKED_INPUT_DTYPE)])
+assert EVAL_RECORD_DTYPE.itemsize == 20 and TRAIN_RECORD_DTYPE.itemsize == 40
+
+
+class NrcError(RuntimeError):
+    pass
+
+
+class nrc_config_t(C.Structure):
+    _fields_ = [("extent_width", C.c_uint32), ("extent_height", C.c_uint32), ("seed", C.c_uint64)]
+
+
+_lib = None
+
+# name -> (restype, argtypes); also the list tests check against the symbols include/nrc_b200.h declares
+SIGNATURES = {
+    "nrc_last_error": (C.c_char_p, []),
+    "nrc_get_eval_record_buffer_size": (C.c_uint64, [C.c_uint32, C.c_uint32]),
+    "nrc_get_batch_train_record_buffer_size": (C.c_uint64, []),
+    "nrc_get_train_batch_count": (C.c_uint32, []),
+    "nrc_get_train_batch_size": (C.c_uint32, []),
+    "nrc_get_weight_count": (C.c_uint32, []),
+    "nrc_get_default_train_probability": (C.c_float, []),
+    "nrc_create": (C.c_int, [C.POINTER(nrc_config_t), C.c_int, C.POINTER(C.c_void_p)]),
+    "nrc_destroy": (None, [C.c_void_p]),
+    "nrc_reset_mlp_buffers": (C.c_int, [C.c_void_p, C.c_uint64]),
+    "nrc_set_weights": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nrc_get_weight_buffer": (C.c_void_p, [C.c_void_p]),
+    "nrc_get_use_weight_buffer": (C.c_void_p, [C.c_void_p]),
+    "nrc_get_optimizer_entry_buffer": (C.c_void_p, [C.c_void_p]),
+    "nrc_get_optimizer_state_buffer": (C.c_void_p, [C.c_void_p]),
+    "nrc_get_gradient_buffer": (C.c_void_p, [C.c_void_p]),
+    "nrc_download": (C.c_int, [C.c_void_p] * 7),
+    "nrc_set_use_ema_weights": (None, [C.c_void_p, C.c_int]),
+    "nrc_is_use_ema_weights": (C.c_int, [C.c_void_p]),
+    "nrc_set_train_probability": (None, [C.c_void_p, C.c_float]),
+    "nrc_get_train_probability": (C.c_float, [C.c_void_p]),
+    "nrc_next_frame": (C.c_uint32, [C.c_void_p]),
+    "nrc_get_seed": (C.c_uint32, [C.c_void_p]),
+    "nrc_mlp_evaluate_encoded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "nrc_mlp_gradient_encoded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]),
+    "nrc_infer_encoded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
+    "nrc_infer_unpacked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "nrc_infer_scatter_unpacked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64,
+                                             C.c_void_p, C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), C.c_void_p]),
+    "nrc_gradient_unpacked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                        C.c_void_p]),
+    "nrc_gradient_encoded": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_int, C.c_void_p]),
+    "nrc_adam_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "nrc_train_batch_unpacked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
+                                           C.c_int, C.c_void_p]),
+    "nrc_set_prediction_capture": (None, [C.c_void_p, C.c_void_p]),
+    "nrc_image_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                       C.c_float, C.c_void_p]),
+    "nrc_image_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+}
+
+
+def lib() -> C.CDLL:
+    """Loads the CUDA library; raises (never falls back) if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NrcError(f"{LIB_PATH} is missing: run `python -m vknrc_b200.build` (needs nvcc). There is no CPU fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = L
+    return _lib
+
+
+def _check(rc: int) -> None:
+    if rc != 0:
+        raise NrcError(f"nrc_b200 error {rc}: {lib().nrc_last_error().decode()}")
+
+
+def _ptr(t) -> int:
+    """Device pointer of a torch CUDA tensor (or None)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "expected a contiguous CUDA tensor"
+    return t.data_ptr()
+
+
+def _stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _DevView:
+    """Zero-copy torch view of library-owned device memory via __cuda_array_interface__."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def mlp_evaluate_encoded(weights, inputs, outputs=None):
+    """launchKernel("evaluate_32.spv", ..., weights, inputs, outputs) (test/main.cpp:116-117)."""
+    import torch
+    n = inputs.shape[0]
+    if outputs is None:
+        outputs = torch.empty((n, 3), dtype=torch.float16, device=inputs.device)
+    _check(lib().nrc_mlp_evaluate_encoded(_ptr(weights), _ptr(inputs), _ptr(outputs), n, _stream()))
+    return outputs
+
+
+def mlp_gradient_encoded(weights, dw, inputs, targets):
+    """launchKernel("train_32.spv", ..., weights, dw, inputs, targets) (test/main.cpp:180-181); dw accumulates."""
+    _check(lib().nrc_mlp_gradient_encoded(_ptr(weights), _ptr(dw), _ptr(inputs), _ptr(targets), inputs.shape[0], _stream()))
+    return dw
+
+
+class NrcState:
+    """Python handle on the C++ ``nrc::NrcState`` (shaped like VkNRCState, src/VkNRCState.hpp:17-90)."""
+
+    def __init__(self, device: int = 0, extent=(1920, 1080), seed: int = 0):
+        self._h = C.c_void_p()
+        cfg = nrc_config_t(extent[0], extent[1], seed)
+        _check(lib().nrc_create(C.byref(cfg), device, C.byref(self._h)))
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().nrc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- statics (src/VkNRCState.hpp:83-89)
+    @staticmethod
+    def get_eval_record_buffer_size(extent) -> int:
+        return lib().nrc_get_eval_record_buffer_size(extent[0], extent[1])
+
+    @staticmethod
+    def get_batch_train_record_buffer_size() -> int:
+        return lib().nrc_get_batch_train_record_buffer_size()
+
+    @staticmethod
+    def get_train_batch_count() -> int:
+        return lib().nrc_get_train_batch_count()
+
+    @staticmethod
+    def get_train_batch_size() -> int:
+        return lib().nrc_get_train_batch_size()
+
+    @staticmethod
+    def get_weight_count() -> int:
+        return lib().nrc_get_weight_count()
+
+    # ---- state
+    def reset_mlp_buffers(self, seed: int):
+        _check(lib().nrc_reset_mlp_buffers(self._h, seed))
+
+    def set_weights(self, fp32_weights: np.ndarray):
+        w = np.ascontiguousarray(fp32_weights, np.float32).reshape(WEIGHT_COUNT)
+        _check(lib().nrc_set_weights(self._h, w.ctypes.data))
+
+    def set_use_ema_weights(self, v: bool):
+        lib().nrc_set_use_ema_weights(self._h, int(v))
+
+    def is_use_ema_weights(self) -> bool:
+        return bool(lib().nrc_is_use_ema_weights(self._h))
+
+    def set_train_probability(self, p: float):
+        lib().nrc_set_train_probability(self._h, p)
+
+    def get_train_probability(self) -> float:
+        return lib().nrc_get_train_probability(self._h)
+
+    def next_frame(self) -> int:
+        return lib().nrc_next_frame(self._h)
+
+    def download(self):
+        """Synchronises the current stream and returns host copies of every persistent buffer."""
+        w = np.empty(WEIGHT_COUNT, np.uint16)
+        uw = np.empty(WEIGHT_COUNT, np.uint16)
+        e = np.empty(WEIGHT_COUNT, OPT_ENTRY_DTYPE)
+        s = np.empty(1, OPT_STATE_DTYPE)
+        g = np.empty(GRADIENT_FLOATS, np.float32)
+        _check(lib().nrc_download(self._h, w.ctypes.data, uw.ctypes.data, e.ctypes.data, s.ctypes.data, g.ctypes.data, _stream()))
+        return {"weights": w.view(np.float16), "use_weights": uw.view(np.float16), "optimizer_entries": e,
+                "optimizer_state": s[0], "gradients": g}
+
+    def gradient_tensor(self):
+        """Zero-copy fp32[20736] torch view of the gradient buffer (what a multi-GPU caller all-reduces)."""
+        import torch
+        return torch.as_tensor(_DevView(lib().nrc_get_gradient_buffer(self._h), (GRADIENT_FLOATS,), "<f4"), device=f"cuda:{self.device}")
+
+    def weight_tensor(self, use: bool = False):
+        import torch
+        p = lib().nrc_get_use_weight_buffer(self._h) if use else lib().nrc_get_weight_buffer(self._h)
+        return torch.as_tensor(_DevView(p, (WEIGHT_COUNT,), "<f2"), device=f"cuda:{self.device}")
+
+    def set_prediction_capture(self, t):
+        lib().nrc_set_prediction_capture(self._h, _ptr(t))
+
+    # ---- inference
+    def infer_encoded(self, inputs, outputs=None, clamp: bool = False):
+        import torch
+        n = inputs.shape[0]
+        if outputs is None:
+            outputs = torch.empty((n, 3), dtype=torch.float16, device=inputs.device)
+        _check(lib().nrc_infer_encoded(self._h, _ptr(inputs), _ptr(outputs), n, int(clamp), _stream()))
+        return outputs
+
+    def infer_unpacked(self, records, count=None, outputs=None, stride_bytes: int = 56, max_count=None):
+        import torch
+        n = records.shape[0] if max_count is None else max_count
+        if outputs is None:
+            outputs = torch.empty((n, 3), dtype=torch.float16, device=records.device)
+        _check(lib().nrc_infer_unpacked(self._h, _ptr(records), stride_bytes, _ptr(count), n, _ptr(outputs), _stream()))
+        return outputs
+
+    def infer_scatter_unpacked(self, dst, records, count, bias_factor_r, factor_gb, image_pitch, train_records,
+                               dst_stride_bytes: int = 4, stride_bytes: int = 56, max_count=None):
+        n = records.shape[0] if max_count is None else max_count
+        ptrs = (C.c_void_p * 4)(*[_ptr(t) for t in train_records])
+        _check(lib().nrc_infer_scatter_unpacked(self._h, _ptr(dst), dst_stride_bytes, _ptr(records), stride_bytes, _ptr(count), n,
+                                                _ptr(bias_factor_r), _ptr(factor_gb), image_pitch, ptrs, _stream()))
+
+    # ---- training
+    def gradient_unpacked(self, inputs, targets, count=None, max_count=None, input_stride: int = 56, target_stride: int = 12):
+        n = inputs.shape[0] if max_count is None else max_count
+        _check(lib().nrc_gradient_unpacked(self._h, _ptr(inputs), input_stride, _ptr(targets), target_stride, _ptr(count), n, _stream()))
+
+    def gradient_encoded(self, inputs, targets16, count=None, max_count=None, relative_loss: bool = False):
+        n = inputs.shape[0] if max_count is None else max_count
+        _check(lib().nrc_gradient_encoded(self._h, _ptr(inputs), _ptr(targets16), _ptr(count), n, int(relative_loss), _stream()))
+
+    def adam_step(self, write_use_weights: bool = True):
+        _check(lib().nrc_adam_step(self._h, int(write_use_weights), _stream()))
+
+    def train_batch_unpacked(self, inputs, targets, count=None, max_count=None, write_use_weights=True, input_stride=56,
+                             target_stride=12):
+        n = inputs.shape[0] if max_count is None else max_count
+        _check(lib().nrc_train_batch_unpacked(self._h, _ptr(inputs), input_stride, _ptr(targets), target_stride, _ptr(count), n,
+                                              int(write_use_weights), _stream()))
+
+    # ---- learn-an-image
+    def image_train_step(self, image_rgba8, seed_x: int, seed_y: int, batch: int = 16384, lr: float = 0.01):
+        h, w = image_rgba8.shape[0], image_rgba8.shape[1]
+        _check(lib().nrc_image_train_step(self._h, _ptr(image_rgba8), w, h, seed_x & 0xFFFFFFFF, seed_y & 0xFFFFFFFF, batch, lr, _stream()))
+
+    def image_infer(self, width: int, out=None):
+        import torch
+        if out is None:
+            out = torch.empty((width, width, 4), dtype=torch.uint8, device=f"cuda:{self.device}")
+        _check(lib().nrc_image_infer(self._h, _ptr(out), width, _stream()))
+        return out

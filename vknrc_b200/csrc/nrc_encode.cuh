@@ -1,0 +1,91 @@
+// nrc_encode.cuh -- input encodings, evaluated per thread (= per sample) and packed straight into the fp16x2
+// registers that become the first layer's A operand.
+//   NRCInputEncode        shader/src/NRCRecord.glsl:47-95
+//   one-blob-32 (image)   test/mlp_learning_an_image/gradient.comp:26-44
+// The quartic kernel is written with explicit round-to-nearest intrinsics so that nvcc cannot contract it into FMAs:
+// every fp32 step then rounds exactly where the GLSL source (and oracle/nrc_oracle.c) rounds.
+#pragma once
+#include "sm100_ptx.cuh"
+
+namespace nrc {
+
+__device__ __forceinline__ float quartic_cdf(float x, float inv_radius) { // NRCRecord.glsl:51-56
+	const float u = __fmul_rn(x, inv_radius);
+	const float u2 = __fmul_rn(u, u);
+	const float u4 = __fmul_rn(u2, u2);
+	const float poly = __fadd_rn(__fsub_rn(1.0f, __fmul_rn(2.0f / 3.0f, u2)), __fmul_rn(1.0f / 5.0f, u4));
+	const float v = __fadd_rn(__fmul_rn(__fmul_rn(15.0f / 16.0f, u), poly), 0.5f);
+	return fminf(fmaxf(v, 0.0f), 1.0f);
+}
+
+// NRCOneBlob4Encode (NRCRecord.glsl:58-63). Bin i is cdf(r_i - x) - cdf(l_i - x) with r_i == l_{i+1}, so the five
+// distinct edge values are evaluated once each.
+__device__ __forceinline__ void oneblob4(float x, float out[4]) {
+	float c[5];
+#pragma unroll
+	for (int i = 0; i < 5; ++i)
+		c[i] = quartic_cdf(__fsub_rn(0.25f * (float)i, x), 4.0f);
+#pragma unroll
+	for (int i = 0; i < 4; ++i)
+		out[i] = __fsub_rn(c[i + 1], c[i]);
+}
+
+// _nrc_tri (NRCRecord.glsl:65-68): 2|mod(x - 1/2, 2) - 1| - 1. Every step except (x - 1/2) is exact in fp32.
+__device__ __forceinline__ float tri(float x) {
+	const float a = x - 0.5f;
+	const float m = a - 2.0f * floorf(a * 0.5f);
+	return 2.0f * fabsf(m - 1.0f) - 1.0f;
+}
+
+// 14 floats (UnpackedNRCInput order) -> 64 features as 32 packed fp16 pairs, slot order NRCRecord.glsl:86-94.
+__device__ __forceinline__ void encode_nrc(const float in[14], uint32_t o[32]) {
+	float f[64];
+#pragma unroll
+	for (int a = 0; a < 3; ++a)
+#pragma unroll
+		for (int k = 0; k < 12; ++k)
+			f[12 * a + k] = tri((float)(1 << k) * in[a]);
+	oneblob4(in[3], f + 36);
+	oneblob4(in[4], f + 40);
+	oneblob4(in[5], f + 44);
+	oneblob4(in[6], f + 48);
+	oneblob4(1.0f - expf(-in[7]), f + 52);
+#pragma unroll
+	for (int i = 0; i < 6; ++i)
+		f[56 + i] = in[8 + i];
+	f[62] = 1.0f, f[63] = 1.0f;
+#pragma unroll
+	for (int i = 0; i < 32; ++i)
+		o[i] = sm100::cvt_pack_f16x2(f[2 * i], f[2 * i + 1]);
+}
+
+// one-blob-32 of u then v; note the mismatched inverse radii 32 / 4 are the reference's (gradient.comp:33-39).
+__device__ __forceinline__ void encode_oneblob32(float u, float v, uint32_t o[32]) {
+#pragma unroll
+	for (int h = 0; h < 2; ++h) {
+		const float x = h ? v : u;
+#pragma unroll
+		for (int i = 0; i < 16; ++i) {
+			const float l0 = (float)(2 * i) / 32.0f, r0 = (float)(2 * i + 1) / 32.0f, r1 = (float)(2 * i + 2) / 32.0f;
+			const float e0 = __fsub_rn(quartic_cdf(__fsub_rn(r0, x), 32.0f), quartic_cdf(__fsub_rn(l0, x), 4.0f));
+			const float e1 = __fsub_rn(quartic_cdf(__fsub_rn(r1, x), 32.0f), quartic_cdf(__fsub_rn(r0, x), 4.0f));
+			o[16 * h + i] = sm100::cvt_pack_f16x2(e0, e1);
+		}
+	}
+}
+
+// pcg2d (test/mlp_learning_an_image/gradient.comp:15-24)
+__device__ __forceinline__ void pcg2d(uint32_t &x, uint32_t &y) {
+	x = x * 1664525u + 1013904223u;
+	y = y * 1664525u + 1013904223u;
+	x += y * 1664525u;
+	y += x * 1664525u;
+	x ^= x >> 16;
+	y ^= y >> 16;
+	x += y * 1664525u;
+	y += x * 1664525u;
+	x ^= x >> 16;
+	y ^= y >> 16;
+}
+
+} // namespace nrc

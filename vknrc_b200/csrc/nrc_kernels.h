@@ -1,0 +1,101 @@
+// nrc_kernels.h -- parameter blocks and launchers shared by the CUDA kernels and the host object (internal).
+#pragma once
+#include <cuda.h> // CUtensorMap (type only; the encode entry point is resolved at run time, libcuda is not linked)
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "nrc_config.h"
+#include "sm100_ptx.cuh"
+
+#ifndef NRC_INFER_SLOTS
+#define NRC_INFER_SLOTS 5 // 128-sample tiles in flight per SM: 5 x (64 accumulator + 32 operand) = 480 of 512 TMEM columns
+#endif
+
+namespace nrc {
+
+enum InMode : int {
+	NRC_IN_ENCODED = 0,   // [n][64] fp16, test/evaluate_NV.comp:18-21
+	NRC_IN_UNPACKED = 1,  // [n] NrcUnpackedInput-shaped records (14 fp32 at a caller-given stride), encode fused
+	NRC_IN_IMAGE_GRID = 2, // learn-an-image inference: uv from the pixel index (inference.comp:33-34)
+	NRC_IN_IMAGE_RANDOM = 3 // learn-an-image training: uv from pcg2d(seed + gid) (gradient.comp:47-48)
+};
+enum OutMode : int {
+	NRC_OUT_F16VEC3 = 0, // [n][3] fp16, test/evaluate_NV.comp:29-30
+	NRC_OUT_SCATTER = 1, // nrc_inference.comp:48-73
+	NRC_OUT_RGBA8 = 2    // mlp_learning_an_image/inference.comp:53
+};
+enum LossKind : int { NRC_LOSS_L2 = 0, NRC_LOSS_RELATIVE_L2_LUMINANCE = 1 };
+
+struct InferParams {
+	uint64_t n;               // number of queries (upper bound when d_count != nullptr)
+	const uint32_t *d_count;  // optional device-resident count
+	int in_mode, out_mode, clamp_output;
+	const void *in;           // NRC_IN_UNPACKED: first record's 14 floats
+	uint32_t in_stride_bytes; // NRC_IN_UNPACKED: bytes between records (56 for a packed array)
+	uint32_t image_width;     // NRC_IN_IMAGE_GRID
+	void *out;                // F16VEC3 / RGBA8
+	const uint32_t *dst;      // SCATTER: eval-record dst words
+	uint32_t dst_stride_u32;  // SCATTER: stride between dst words in u32 (5 inside an NrcEvalRecord array, 1 if packed)
+	void *bias_factor_r;      // SCATTER: rgba32f image, read-modify-write
+	const void *factor_gb;    // SCATTER: rg32f image
+	uint32_t image_pitch;     // SCATTER: pixels per image row
+	void *train_records[NRC_TRAIN_BATCH_COUNT];
+};
+
+struct GradParams {
+	uint64_t n;              // records in this batch (upper bound when d_count != nullptr)
+	const uint32_t *d_count; // optional device-resident count (clamped to n)
+	int in_mode, loss_kind;
+	float loss_scale;
+	const void *in;          // ENCODED: unused (TMA); UNPACKED: 14 floats per record at in_stride_bytes
+	uint32_t in_stride_bytes;
+	const void *target;      // ENCODED: [n][3] fp16 (test/train_NV.comp:11-16); UNPACKED: 3 fp32 at target_stride_bytes
+	uint32_t target_stride_bytes;
+	int target_is_f16;
+	// learn-an-image (gradient.comp:46-50)
+	uint32_t seed_x, seed_y;
+	const uint8_t *image_rgba8;
+	uint32_t image_w, image_h;
+	float *partials;         // [gridDim.x][NRC_GRAD_STRIDE] per-CTA partial dW (+ loss, count slots)
+	void *y_out;             // optional [n][3] fp32 predictions (unclamped), for loss-curve checks
+};
+
+struct ReduceParams {
+	const float *partials;
+	uint32_t num_partials;
+	float *gradients;      // [NRC_GRAD_STRIDE]
+	int accumulate;        // 1: gradients += sum (test/train_NV.comp semantics), 0: gradients = sum
+	uint32_t limit;        // number of leading elements to produce (20672 for a caller's dW, NRC_GRAD_STRIDE otherwise)
+	// fused nrc_train_prepare.comp:16-28 (done by one thread; all optional)
+	uint32_t *d_count;     // clamped in place to batch_cap
+	uint32_t batch_cap;
+	NrcOptimizerState *opt_state;
+};
+
+struct AdamParams {
+	const float *gradients;          // [NRC_GRAD_STRIDE]; the divisor is gradients[NRC_GRAD_COUNT_SLOT]
+	NrcOptimizerEntry *entries;
+	NrcOptimizerState *opt_state;    // advanced in place (nrc_train_prepare.comp:22-28) by the last CTA to finish
+	uint32_t *done_counter;          // zero-initialised device word owned by the state object
+	__half *weights;                 // fp16, reference layout
+	__half *use_weights;             // nullptr = the non-WRITE_USE_WEIGHTS variant
+	int use_ema;
+};
+
+struct SgdParams { // mlp_learning_an_image/optimize.comp:21-29
+	const float *gradients;
+	NrcOptimizerEntry *entries; // fp32 master weights live in entries[i].weight
+	__half *weights;
+	float lr, batch;
+};
+
+cudaError_t launch_infer(const InferParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream);
+// returns the number of CTAs (= partial rows) through *num_partials
+cudaError_t launch_gradient(const GradParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, uint32_t *num_partials,
+                            cudaStream_t stream);
+cudaError_t launch_reduce(const ReduceParams &p, cudaStream_t stream);
+cudaError_t launch_adam(const AdamParams &p, cudaStream_t stream);
+cudaError_t launch_sgd(const SgdParams &p, cudaStream_t stream);
+uint32_t gradient_max_partials(int sms);
+
+} // namespace nrc

@@ -1,0 +1,470 @@
+// nrc_state.cu -- NrcState (the VkNRCState-shaped host object) and the C ABI declared in include/nrc_b200.h.
+#include "nrc_state.hpp"
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "../../include/nrc_b200.h"
+
+namespace nrc {
+
+// ---------------------------------------------------------------------------------------------------- error plumbing
+static thread_local std::string g_last_error;
+static int set_error(int code, const std::string &what) {
+	g_last_error = what;
+	return code;
+}
+#define NRC_CUDA_TRY(expr, errsink)                                                                                   \
+	do {                                                                                                               \
+		cudaError_t e_ = (expr);                                                                                       \
+		if (e_ != cudaSuccess)                                                                                         \
+			return errsink(e_ == cudaErrorMemoryAllocation ? NRC_ERR_OUT_OF_MEMORY : NRC_ERR_CUDA,                     \
+			               std::string(#expr) + ": " + cudaGetErrorString(e_));                                         \
+	} while (0)
+
+// ---------------------------------------------------------------------------------------------------- tensor maps
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                    const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static PFN_encodeTiled encode_fn() {
+	static PFN_encodeTiled fn = [] {
+		void *p = nullptr;
+		cudaDriverEntryPointQueryResult q;
+		if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+			p = nullptr;
+		return (PFN_encodeTiled)p;
+	}();
+	return fn;
+}
+// [rows][64] fp16 row-major tensor, box = box_rows x 64, 128-byte swizzle, out-of-bounds rows read as zero.
+static int make_map(CUtensorMap *tm, const void *base, uint64_t rows, uint32_t box_rows, std::string *err) {
+	PFN_encodeTiled fn = encode_fn();
+	if (!fn) {
+		*err = "cuTensorMapEncodeTiled is not available from this driver";
+		return NRC_ERR_CUDA;
+	}
+	if (((uintptr_t)base & 15u) != 0) {
+		*err = "fp16 matrix base address must be 16-byte aligned";
+		return NRC_ERR_INVALID_ARGUMENT;
+	}
+	const cuuint64_t gdim[2] = {64, rows ? rows : 1};
+	const cuuint64_t gstride[1] = {128};
+	const cuuint32_t box[2] = {64, box_rows};
+	const cuuint32_t estride[2] = {1, 1};
+	CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void *>(base), gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+	                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+	if (r != CUDA_SUCCESS) {
+		*err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+		return NRC_ERR_CUDA;
+	}
+	return NRC_OK;
+}
+int make_weight_tensor_map(CUtensorMap *tm, const void *d_weights, std::string *err) {
+	return make_map(tm, d_weights, NRC_WEIGHT_ROWS, 64, err);
+}
+int make_input_tensor_map(CUtensorMap *tm, const void *d_inputs, uint64_t rows, std::string *err) {
+	return make_map(tm, d_inputs, rows, NRC_TILE, err);
+}
+
+static int check_device(int device, int *sms, std::string *err) {
+	cudaDeviceProp prop;
+	cudaError_t e = cudaGetDeviceProperties(&prop, device);
+	if (e != cudaSuccess) {
+		*err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
+		return NRC_ERR_CUDA;
+	}
+	if (prop.major != 10) { // the kernels are sm_100a-only (tcgen05 / TMEM); there is deliberately no other path
+		*err = std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+		       "; this library only runs on sm_100 (B200)";
+		return NRC_ERR_UNSUPPORTED_DEVICE;
+	}
+	*sms = prop.multiProcessorCount;
+	return NRC_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------- NrcState
+int NrcState::fail(int code, const std::string &what) {
+	m_error_code = code;
+	m_error = what;
+	return set_error(code, what);
+}
+
+NrcState::NrcState(int device, Extent2D extent, uint64_t seed) : m_device(device), m_extent(extent), m_rng((uint32_t)seed) {
+	std::string err;
+	int rc = check_device(device, &m_sms, &err);
+	if (rc != NRC_OK) {
+		fail(rc, err);
+		return;
+	}
+	auto alloc = [&](void **p, size_t bytes) {
+		cudaError_t e = cudaMalloc(p, bytes);
+		if (e != cudaSuccess) {
+			fail(e == cudaErrorMemoryAllocation ? NRC_ERR_OUT_OF_MEMORY : NRC_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+			return false;
+		}
+		return cudaMemset(*p, 0, bytes) == cudaSuccess;
+	};
+	if (cudaSetDevice(device) != cudaSuccess) {
+		fail(NRC_ERR_CUDA, "cudaSetDevice failed");
+		return;
+	}
+	// weights are padded to whole 64-row TMA boxes so that no box of the weight tensor map leaves the allocation
+	const size_t wbytes = (size_t)NRC_LAYERS * 64 * 64 * sizeof(__half);
+	if (!alloc((void **)&m_weights, wbytes) || !alloc((void **)&m_use_weights, wbytes) ||
+	    !alloc((void **)&m_optimizer_state, sizeof(NrcOptimizerState)) ||
+	    !alloc((void **)&m_optimizer_entries, sizeof(NrcOptimizerEntry) * NRC_WEIGHT_COUNT) ||
+	    !alloc((void **)&m_gradients, sizeof(float) * NRC_GRAD_STRIDE) ||
+	    !alloc((void **)&m_partials, sizeof(float) * NRC_GRAD_STRIDE * gradient_max_partials(m_sms)) ||
+	    !alloc((void **)&m_done_counter, sizeof(uint32_t)))
+		return;
+	m_ok = true;
+	if (ResetMLPBuffers(seed) != NRC_OK)
+		m_ok = false;
+}
+
+NrcState::~NrcState() {
+	cudaFree(m_weights), cudaFree(m_use_weights), cudaFree(m_optimizer_state), cudaFree(m_optimizer_entries);
+	cudaFree(m_gradients), cudaFree(m_partials), cudaFree(m_done_counter);
+}
+
+// src/VkNRCState.cpp:39-44 (He-normal, sigma = sqrt(2 / 64)) and :46-58 (fp32 master = ema = init, fp16 copy RNE)
+int NrcState::ResetMLPBuffers(uint64_t seed) {
+	std::mt19937 rng((uint32_t)seed);
+	std::normal_distribution<float> norm{0, std::sqrt(2.0f / float(kNNWidth))};
+	std::vector<float> w(NRC_WEIGHT_COUNT);
+	for (auto &x : w)
+		x = norm(rng);
+	return upload_initial(w.data());
+}
+int NrcState::SetWeights(const float *fp32_weights) {
+	if (!fp32_weights)
+		return fail(NRC_ERR_INVALID_ARGUMENT, "SetWeights: null weights");
+	return upload_initial(fp32_weights);
+}
+int NrcState::upload_initial(const float *w) {
+	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
+	std::vector<__half> h(NRC_WEIGHT_COUNT);
+	std::vector<NrcOptimizerEntry> e(NRC_WEIGHT_COUNT);
+	for (uint32_t i = 0; i < NRC_WEIGHT_COUNT; ++i) {
+		h[i] = __float2half_rn(w[i]);
+		e[i] = NrcOptimizerEntry{0.0f, 0.0f, w[i], w[i]};
+	}
+	const NrcOptimizerState st{0u, 1.0f, 1.0f, 1.0f, 0.0f}; // src/VkNRCState.cpp:50
+	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
+	NRC_CUDA_TRY(cudaMemcpy(m_weights, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice), sink);
+	NRC_CUDA_TRY(cudaMemcpy(m_use_weights, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice), sink);
+	NRC_CUDA_TRY(cudaMemcpy(m_optimizer_entries, e.data(), e.size() * sizeof(NrcOptimizerEntry), cudaMemcpyHostToDevice), sink);
+	NRC_CUDA_TRY(cudaMemcpy(m_optimizer_state, &st, sizeof(st), cudaMemcpyHostToDevice), sink);
+	NRC_CUDA_TRY(cudaMemset(m_done_counter, 0, sizeof(uint32_t)), sink);
+	return NRC_OK;
+}
+
+int NrcState::Download(uint16_t *weights, uint16_t *use_weights, void *entries, void *state, float *gradients, cudaStream_t stream) {
+	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
+	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
+	NRC_CUDA_TRY(cudaStreamSynchronize(stream), sink);
+	if (weights)
+		NRC_CUDA_TRY(cudaMemcpy(weights, m_weights, NRC_WEIGHT_COUNT * 2, cudaMemcpyDeviceToHost), sink);
+	if (use_weights)
+		NRC_CUDA_TRY(cudaMemcpy(use_weights, m_use_weights, NRC_WEIGHT_COUNT * 2, cudaMemcpyDeviceToHost), sink);
+	if (entries)
+		NRC_CUDA_TRY(cudaMemcpy(entries, m_optimizer_entries, NRC_WEIGHT_COUNT * sizeof(NrcOptimizerEntry), cudaMemcpyDeviceToHost), sink);
+	if (state)
+		NRC_CUDA_TRY(cudaMemcpy(state, m_optimizer_state, sizeof(NrcOptimizerState), cudaMemcpyDeviceToHost), sink);
+	if (gradients)
+		NRC_CUDA_TRY(cudaMemcpy(gradients, m_gradients, NRC_GRAD_STRIDE * sizeof(float), cudaMemcpyDeviceToHost), sink);
+	return NRC_OK;
+}
+
+int NrcState::Infer(InferParams p, const void *encoded_inputs, const __half *weights, cudaStream_t stream) {
+	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
+	if (p.n == 0)
+		return NRC_OK;
+	CUtensorMap tm_w, tm_in;
+	std::string err;
+	int rc = make_weight_tensor_map(&tm_w, weights, &err);
+	if (rc == NRC_OK)
+		rc = p.in_mode == NRC_IN_ENCODED ? make_input_tensor_map(&tm_in, encoded_inputs, p.n, &err) : (tm_in = tm_w, NRC_OK);
+	if (rc != NRC_OK)
+		return fail(rc, err);
+	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
+	NRC_CUDA_TRY(launch_infer(p, tm_w, tm_in, m_sms, stream), sink);
+	return NRC_OK;
+}
+
+int NrcState::Gradient(GradParams p, const void *encoded_inputs, const __half *weights, float *gradients, bool accumulate, uint32_t *d_count,
+                       uint32_t batch_cap, cudaStream_t stream) {
+	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
+	CUtensorMap tm_w, tm_in;
+	std::string err;
+	int rc = make_weight_tensor_map(&tm_w, weights, &err);
+	if (rc == NRC_OK)
+		rc = p.in_mode == NRC_IN_ENCODED ? make_input_tensor_map(&tm_in, encoded_inputs, p.n, &err) : (tm_in = tm_w, NRC_OK);
+	if (rc != NRC_OK)
+		return fail(rc, err);
+	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
+	p.partials = m_partials;
+	p.d_count = d_count;
+	uint32_t num_partials = 0;
+	NRC_CUDA_TRY(launch_gradient(p, tm_w, tm_in, m_sms, &num_partials, stream), sink);
+	ReduceParams r{};
+	r.partials = m_partials, r.num_partials = num_partials, r.gradients = gradients, r.accumulate = accumulate ? 1 : 0;
+	r.limit = accumulate ? NRC_WEIGHT_COUNT : NRC_GRAD_STRIDE;
+	r.d_count = d_count, r.batch_cap = batch_cap;
+	NRC_CUDA_TRY(launch_reduce(r, stream), sink);
+	return NRC_OK;
+}
+
+int NrcState::AdamStep(bool write_use_weights, cudaStream_t stream) {
+	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
+	AdamParams a{};
+	a.gradients = m_gradients, a.entries = m_optimizer_entries, a.opt_state = m_optimizer_state, a.done_counter = m_done_counter;
+	a.weights = m_weights, a.use_weights = write_use_weights ? m_use_weights : nullptr, a.use_ema = m_use_ema_weights ? 1 : 0;
+	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
+	NRC_CUDA_TRY(launch_adam(a, stream), sink);
+	return NRC_OK;
+}
+
+int NrcState::SgdStep(float lr, float batch, cudaStream_t stream) {
+	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
+	SgdParams s{};
+	s.gradients = m_gradients, s.entries = m_optimizer_entries, s.weights = m_weights, s.lr = lr, s.batch = batch;
+	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
+	NRC_CUDA_TRY(launch_sgd(s, stream), sink);
+	return NRC_OK;
+}
+
+} // namespace nrc
+
+// ====================================================================================================== C ABI
+using namespace nrc;
+struct nrc_state_t {
+	NrcState state;
+	nrc_state_t(int device, Extent2D e, uint64_t seed) : state(device, e, seed) {}
+};
+
+static int bad_arg(const char *what) { return set_error(NRC_ERR_INVALID_ARGUMENT, what); }
+#define NRC_REQUIRE(cond, msg)                                                                                         \
+	do {                                                                                                               \
+		if (!(cond))                                                                                                   \
+			return bad_arg(msg);                                                                                       \
+	} while (0)
+
+extern "C" {
+
+const char *nrc_last_error(void) { return g_last_error.c_str(); }
+
+uint64_t nrc_get_eval_record_buffer_size(uint32_t w, uint32_t h) { return NrcState::GetEvalRecordBufferSize({w, h}); }
+uint64_t nrc_get_batch_train_record_buffer_size(void) { return NrcState::GetBatchTrainRecordBufferSize(); }
+uint32_t nrc_get_train_batch_count(void) { return NrcState::GetTrainBatchCount(); }
+uint32_t nrc_get_train_batch_size(void) { return NrcState::GetTrainBatchSize(); }
+uint32_t nrc_get_weight_count(void) { return NrcState::GetWeightCount(); }
+float nrc_get_default_train_probability(void) { return NrcState::GetDefaultTrainProbability(); }
+
+int nrc_create(const nrc_config_t *config, int device, nrc_handle_t *out) {
+	NRC_REQUIRE(config && out, "nrc_create: null argument");
+	*out = nullptr;
+	nrc_state_t *h = new (std::nothrow) nrc_state_t(device, Extent2D{config->extent_width, config->extent_height}, config->seed);
+	if (!h)
+		return set_error(NRC_ERR_OUT_OF_MEMORY, "nrc_create: host allocation failed");
+	if (!h->state.ok()) {
+		const int code = h->state.error_code();
+		const std::string msg = h->state.error();
+		delete h;
+		return set_error(code ? code : NRC_ERR_CUDA, msg);
+	}
+	*out = h;
+	return NRC_OK;
+}
+void nrc_destroy(nrc_handle_t h) { delete h; }
+
+int nrc_reset_mlp_buffers(nrc_handle_t h, uint64_t seed) {
+	NRC_REQUIRE(h, "null handle");
+	return h->state.ResetMLPBuffers(seed);
+}
+int nrc_set_weights(nrc_handle_t h, const float *w) {
+	NRC_REQUIRE(h, "null handle");
+	return h->state.SetWeights(w);
+}
+void *nrc_get_weight_buffer(nrc_handle_t h) { return h ? h->state.GetWeightBuffer() : nullptr; }
+void *nrc_get_use_weight_buffer(nrc_handle_t h) { return h ? h->state.GetUseWeightBuffer() : nullptr; }
+void *nrc_get_optimizer_entry_buffer(nrc_handle_t h) { return h ? h->state.GetOptimizerEntryBuffer() : nullptr; }
+void *nrc_get_optimizer_state_buffer(nrc_handle_t h) { return h ? h->state.GetOptimizerStateBuffer() : nullptr; }
+void *nrc_get_gradient_buffer(nrc_handle_t h) { return h ? h->state.GetGradientBuffer() : nullptr; }
+int nrc_download(nrc_handle_t h, uint16_t *weights, uint16_t *use_weights, void *entries, void *state, float *gradients, void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	return h->state.Download(weights, use_weights, entries, state, gradients, (cudaStream_t)stream);
+}
+void nrc_set_use_ema_weights(nrc_handle_t h, int v) {
+	if (h)
+		h->state.SetUseEMAWeights(v != 0);
+}
+int nrc_is_use_ema_weights(nrc_handle_t h) { return h && h->state.IsUseEMAWeights(); }
+void nrc_set_train_probability(nrc_handle_t h, float p) {
+	if (h)
+		h->state.SetTrainProbability(p);
+}
+float nrc_get_train_probability(nrc_handle_t h) { return h ? h->state.GetTrainProbability() : 0.0f; }
+uint32_t nrc_next_frame(nrc_handle_t h) { return h ? h->state.NextFrame() : 0u; }
+uint32_t nrc_get_seed(nrc_handle_t h) { return h ? h->state.GetSeed() : 0u; }
+void nrc_set_prediction_capture(nrc_handle_t h, float *d) {
+	if (h)
+		h->state.SetPredictionCapture(d);
+}
+
+// ---- handle-less test-harness kernels: a lazily created per-device scratch state supplies the partial buffers
+static NrcState *scratch_state(int *rc) {
+	static std::mutex mu;
+	static std::vector<NrcState *> per_device;
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) {
+		*rc = set_error(NRC_ERR_CUDA, "cudaGetDevice failed");
+		return nullptr;
+	}
+	std::lock_guard<std::mutex> lock(mu);
+	if ((int)per_device.size() <= dev)
+		per_device.resize(dev + 1, nullptr);
+	if (!per_device[dev]) {
+		NrcState *s = new (std::nothrow) NrcState(dev, Extent2D{0, 0}, 0);
+		if (!s || !s->ok()) {
+			*rc = set_error(s ? s->error_code() : NRC_ERR_OUT_OF_MEMORY, s ? s->error() : "host allocation failed");
+			delete s;
+			return nullptr;
+		}
+		per_device[dev] = s;
+	}
+	return per_device[dev];
+}
+
+int nrc_mlp_evaluate_encoded(const void *d_weights, const void *d_inputs, void *d_outputs, uint64_t n, void *stream) {
+	if (n == 0)
+		return NRC_OK;
+	NRC_REQUIRE(d_weights && d_inputs && d_outputs, "nrc_mlp_evaluate_encoded: null buffer");
+	int rc = NRC_OK;
+	NrcState *s = scratch_state(&rc);
+	if (!s)
+		return rc;
+	InferParams p{};
+	p.n = n, p.in_mode = NRC_IN_ENCODED, p.out_mode = NRC_OUT_F16VEC3, p.clamp_output = 0, p.out = d_outputs;
+	return s->Infer(p, d_inputs, (const __half *)d_weights, (cudaStream_t)stream);
+}
+
+int nrc_mlp_gradient_encoded(const void *d_weights, float *d_dw, const void *d_inputs, const void *d_targets, uint64_t n, void *stream) {
+	if (n == 0)
+		return NRC_OK;
+	NRC_REQUIRE(d_weights && d_dw && d_inputs && d_targets, "nrc_mlp_gradient_encoded: null buffer");
+	int rc = NRC_OK;
+	NrcState *s = scratch_state(&rc);
+	if (!s)
+		return rc;
+	GradParams p{};
+	p.n = n, p.in_mode = NRC_IN_ENCODED, p.loss_kind = NRC_LOSS_L2, p.loss_scale = 1.0f;
+	p.target = d_targets, p.target_stride_bytes = 6, p.target_is_f16 = 1;
+	return s->Gradient(p, d_inputs, (const __half *)d_weights, d_dw, /*accumulate=*/true, nullptr, 0, (cudaStream_t)stream);
+}
+
+int nrc_infer_encoded(nrc_handle_t h, const void *d_inputs, void *d_out, uint64_t n, int clamp_output, void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	if (n == 0)
+		return NRC_OK;
+	NRC_REQUIRE(d_inputs && d_out, "nrc_infer_encoded: null buffer");
+	InferParams p{};
+	p.n = n, p.in_mode = NRC_IN_ENCODED, p.out_mode = NRC_OUT_F16VEC3, p.clamp_output = clamp_output, p.out = d_out;
+	return h->state.Infer(p, d_inputs, h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
+}
+
+int nrc_infer_unpacked(nrc_handle_t h, const void *d_records, uint32_t stride_bytes, const uint32_t *d_count, uint64_t max_count,
+                       void *d_out, void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	if (max_count == 0)
+		return NRC_OK;
+	NRC_REQUIRE(d_records && d_out, "nrc_infer_unpacked: null buffer");
+	NRC_REQUIRE(stride_bytes >= 56 && stride_bytes % 8 == 0 && ((uintptr_t)d_records & 7u) == 0, "nrc_infer_unpacked: records must be 8-byte aligned, stride >= 56 and a multiple of 8");
+	InferParams p{};
+	p.n = max_count, p.d_count = d_count, p.in_mode = NRC_IN_UNPACKED, p.out_mode = NRC_OUT_F16VEC3, p.clamp_output = 1;
+	p.in = d_records, p.in_stride_bytes = stride_bytes, p.out = d_out;
+	return h->state.Infer(p, nullptr, h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
+}
+
+int nrc_infer_scatter_unpacked(nrc_handle_t h, const uint32_t *d_dst, uint32_t dst_stride_bytes, const void *d_records, uint32_t stride_bytes,
+                               const uint32_t *d_count, uint64_t max_count, void *d_bias_factor_r, const void *d_factor_gb,
+                               uint32_t image_pitch, void *const d_train_records[4], void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	if (max_count == 0)
+		return NRC_OK;
+	NRC_REQUIRE(d_dst && d_records, "nrc_infer_scatter_unpacked: null buffer");
+	NRC_REQUIRE(dst_stride_bytes >= 4 && dst_stride_bytes % 4 == 0, "nrc_infer_scatter_unpacked: dst stride must be a multiple of 4");
+	NRC_REQUIRE(stride_bytes >= 56 && stride_bytes % 8 == 0 && ((uintptr_t)d_records & 7u) == 0, "nrc_infer_scatter_unpacked: records must be 8-byte aligned, stride >= 56 and a multiple of 8");
+	InferParams p{};
+	p.n = max_count, p.d_count = d_count, p.in_mode = NRC_IN_UNPACKED, p.out_mode = NRC_OUT_SCATTER, p.clamp_output = 1;
+	p.in = d_records, p.in_stride_bytes = stride_bytes;
+	p.dst = d_dst, p.dst_stride_u32 = dst_stride_bytes / 4;
+	p.bias_factor_r = d_bias_factor_r, p.factor_gb = d_factor_gb, p.image_pitch = image_pitch;
+	for (int b = 0; b < NRC_TRAIN_BATCH_COUNT; ++b)
+		p.train_records[b] = d_train_records ? d_train_records[b] : nullptr;
+	return h->state.Infer(p, nullptr, h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
+}
+
+int nrc_gradient_unpacked(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets, uint32_t target_stride,
+                          uint32_t *d_count, uint32_t max_count, void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	NRC_REQUIRE(max_count == 0 || (d_inputs && d_targets), "nrc_gradient_unpacked: null buffer");
+	NRC_REQUIRE(input_stride >= 56 && input_stride % 8 == 0 && ((uintptr_t)d_inputs & 7u) == 0, "nrc_gradient_unpacked: inputs must be 8-byte aligned, stride >= 56 and a multiple of 8");
+	NRC_REQUIRE(target_stride >= 12 && target_stride % 4 == 0, "nrc_gradient_unpacked: target stride must be >= 12 and a multiple of 4");
+	GradParams p{};
+	p.n = max_count, p.in_mode = NRC_IN_UNPACKED, p.loss_kind = NRC_LOSS_RELATIVE_L2_LUMINANCE, p.loss_scale = NRC_LOSS_SCALE;
+	p.in = d_inputs, p.in_stride_bytes = input_stride, p.target = d_targets, p.target_stride_bytes = target_stride, p.target_is_f16 = 0;
+	p.y_out = h->state.GetPredictionCapture();
+	return h->state.Gradient(p, nullptr, h->state.GetWeightBuffer(), h->state.GetGradientBuffer(), false, d_count, max_count, (cudaStream_t)stream);
+}
+
+int nrc_gradient_encoded(nrc_handle_t h, const void *d_inputs, const void *d_targets, uint32_t *d_count, uint32_t max_count, int relative_loss,
+                         void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	NRC_REQUIRE(max_count == 0 || (d_inputs && d_targets), "nrc_gradient_encoded: null buffer");
+	GradParams p{};
+	p.n = max_count, p.in_mode = NRC_IN_ENCODED, p.loss_kind = relative_loss ? NRC_LOSS_RELATIVE_L2_LUMINANCE : NRC_LOSS_L2;
+	p.loss_scale = NRC_LOSS_SCALE, p.target = d_targets, p.target_stride_bytes = 6, p.target_is_f16 = 1;
+	p.y_out = h->state.GetPredictionCapture();
+	return h->state.Gradient(p, d_inputs, h->state.GetWeightBuffer(), h->state.GetGradientBuffer(), false, d_count, max_count, (cudaStream_t)stream);
+}
+
+int nrc_adam_step(nrc_handle_t h, int write_use_weights, void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	return h->state.AdamStep(write_use_weights != 0, (cudaStream_t)stream);
+}
+
+int nrc_train_batch_unpacked(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets, uint32_t target_stride,
+                             uint32_t *d_count, uint32_t max_count, int write_use_weights, void *stream) {
+	int rc = nrc_gradient_unpacked(h, d_inputs, input_stride, d_targets, target_stride, d_count, max_count, stream);
+	if (rc != NRC_OK)
+		return rc;
+	return nrc_adam_step(h, write_use_weights, stream);
+}
+
+int nrc_image_train_step(nrc_handle_t h, const void *d_image_rgba8, uint32_t image_w, uint32_t image_h, uint32_t seed_x, uint32_t seed_y,
+                         uint32_t batch, float lr, void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	NRC_REQUIRE(d_image_rgba8 && image_w && image_h && batch, "nrc_image_train_step: bad image or batch");
+	GradParams p{};
+	p.n = batch, p.in_mode = NRC_IN_IMAGE_RANDOM, p.loss_kind = NRC_LOSS_L2, p.loss_scale = 1.0f;
+	p.seed_x = seed_x, p.seed_y = seed_y, p.image_rgba8 = (const uint8_t *)d_image_rgba8, p.image_w = image_w, p.image_h = image_h;
+	p.y_out = h->state.GetPredictionCapture();
+	int rc = h->state.Gradient(p, nullptr, h->state.GetWeightBuffer(), h->state.GetGradientBuffer(), false, nullptr, 0, (cudaStream_t)stream);
+	if (rc != NRC_OK)
+		return rc;
+	return h->state.SgdStep(lr, (float)batch, (cudaStream_t)stream);
+}
+
+int nrc_image_infer(nrc_handle_t h, void *d_out_rgba8, uint32_t width, void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	NRC_REQUIRE(d_out_rgba8 && width, "nrc_image_infer: bad output");
+	InferParams p{};
+	p.n = (uint64_t)width * width, p.in_mode = NRC_IN_IMAGE_GRID, p.out_mode = NRC_OUT_RGBA8, p.image_width = width, p.out = d_out_rgba8;
+	return h->state.Infer(p, nullptr, h->state.GetWeightBuffer(), (cudaStream_t)stream);
+}
+
+} // extern "C"

@@ -1,0 +1,106 @@
+// nrc_state.hpp -- host object of the NRC hot path, shaped like the reference's VkNRCState
+// (src/VkNRCState.hpp:17-90): it owns the persistent MLP buffers (weights, use_weights, optimizer state/entries),
+// the flags the UI toggles, and exposes Evaluate/Train entry points that enqueue the sm_100a kernels on the caller's
+// stream. Per-frame record / count / image buffers stay caller-owned, as in the reference's render graph
+// (src/rg/NRCRenderGraph.cpp:139-175).
+#pragma once
+#include <random>
+#include <string>
+
+#include "nrc_kernels.h"
+
+namespace nrc {
+
+struct Extent2D {
+	uint32_t width, height;
+};
+
+class NrcState final {
+public:
+	static constexpr float kDefaultTrainProbability = 0.03f; // src/VkNRCState.hpp:22
+	static constexpr uint32_t kNNHiddenLayers = NRC_HIDDEN_LAYERS, kNNWidth = NRC_WIDTH, kNNOutWidth = NRC_OUT_WIDTH,
+	                          kTrainBatchSize = NRC_TRAIN_BATCH_SIZE, kTrainBatchCount = NRC_TRAIN_BATCH_COUNT;
+	static constexpr uint32_t kNNWeighCount = NRC_WEIGHT_COUNT;
+
+	// throws nothing: on failure `ok()` is false and `error()` explains why
+	NrcState(int device, Extent2D extent, uint64_t seed);
+	~NrcState();
+	NrcState(const NrcState &) = delete;
+	NrcState &operator=(const NrcState &) = delete;
+
+	bool ok() const { return m_ok; }
+	int error_code() const { return m_error_code; }
+	const std::string &error() const { return m_error; }
+
+	// ---- getters, as VkNRCState::Get*Buffer (src/VkNRCState.hpp:43-46)
+	__half *GetWeightBuffer() const { return m_weights; }
+	__half *GetUseWeightBuffer() const { return m_use_weights; }
+	NrcOptimizerEntry *GetOptimizerEntryBuffer() const { return m_optimizer_entries; }
+	NrcOptimizerState *GetOptimizerStateBuffer() const { return m_optimizer_state; }
+	float *GetGradientBuffer() const { return m_gradients; }
+
+	bool IsUseEMAWeights() const { return m_use_ema_weights; }
+	void SetUseEMAWeights(bool v) { m_use_ema_weights = v; }
+	float GetTrainProbability() const { return m_train_probability; }
+	void SetTrainProbability(float p) { m_train_probability = p; }
+	uint32_t GetSeed() const { return m_seed; }
+	uint32_t NextFrame() { // src/VkNRCState.hpp:74-78
+		m_seed = std::uniform_int_distribution<uint32_t>{0}(m_rng);
+		return m_seed;
+	}
+
+	// ---- statics (src/VkNRCState.hpp:83-89, src/VkNRCState.cpp:34-37)
+	static uint64_t GetEvalRecordBufferSize(Extent2D extent) {
+		return ((uint64_t)extent.width * extent.height + (uint64_t)kTrainBatchSize * kTrainBatchCount) * sizeof(NrcEvalRecord);
+	}
+	static uint64_t GetBatchTrainRecordBufferSize() { return (uint64_t)kTrainBatchSize * sizeof(NrcTrainRecord); }
+	static constexpr uint32_t GetTrainBatchCount() { return kTrainBatchCount; }
+	static constexpr uint32_t GetTrainBatchSize() { return kTrainBatchSize; }
+	static constexpr uint32_t GetWeightCount() { return kNNWeighCount; }
+	static constexpr float GetDefaultTrainProbability() { return kDefaultTrainProbability; }
+
+	// ---- (re)initialisation: ResetMLPBuffers (src/VkNRCState.cpp:46-88)
+	int ResetMLPBuffers(uint64_t seed);
+	int SetWeights(const float *fp32_weights);
+	int Download(uint16_t *weights, uint16_t *use_weights, void *entries, void *state, float *gradients, cudaStream_t stream);
+
+	// ---- hot path
+	int Infer(InferParams p, const void *encoded_inputs, const __half *weights, cudaStream_t stream);
+	int Gradient(GradParams p, const void *encoded_inputs, const __half *weights, float *gradients, bool accumulate, uint32_t *d_count,
+	             uint32_t batch_cap, cudaStream_t stream);
+	int AdamStep(bool write_use_weights, cudaStream_t stream);
+	int SgdStep(float lr, float batch, cudaStream_t stream);
+	void SetPredictionCapture(float *d) { m_prediction_capture = d; }
+	float *GetPredictionCapture() const { return m_prediction_capture; }
+
+	int device() const { return m_device; }
+	int sm_count() const { return m_sms; }
+
+private:
+	int fail(int code, const std::string &what);
+	int upload_initial(const float *fp32_weights);
+
+	int m_device{0}, m_sms{0};
+	Extent2D m_extent{};
+	bool m_ok{false};
+	int m_error_code{0};
+	std::string m_error;
+
+	__half *m_weights{nullptr}, *m_use_weights{nullptr};
+	NrcOptimizerState *m_optimizer_state{nullptr};
+	NrcOptimizerEntry *m_optimizer_entries{nullptr};
+	float *m_gradients{nullptr}, *m_partials{nullptr};
+	uint32_t *m_done_counter{nullptr};
+	float *m_prediction_capture{nullptr};
+
+	uint32_t m_seed{0};
+	std::mt19937 m_rng;
+	bool m_use_ema_weights{false};
+	float m_train_probability{kDefaultTrainProbability};
+};
+
+// shared by the handle-less test-harness entry points
+int make_weight_tensor_map(CUtensorMap *tm, const void *d_weights, std::string *err);
+int make_input_tensor_map(CUtensorMap *tm, const void *d_inputs, uint64_t rows, std::string *err);
+
+} // namespace nrc
