@@ -95,7 +95,7 @@ __global__ void __launch_bounds__((NT * 4 + 2) * 32, 1)
 		for (int i = 0; i < kStages; ++i)
 			mbar_init(in_full + i, 1), mbar_init(in_empty + i, 1);
 		for (int i = 0; i < NT; ++i)
-			mbar_init(d_full + i, 1), mbar_init(a_full + i, 128);
+			mbar_init(d_full + i, 1), mbar_init(a_full + i, 4);
 		fence_mbar_init();
 	}
 	if (warp == TMA_WARP)
@@ -130,10 +130,7 @@ __global__ void __launch_bounds__((NT * 4 + 2) * 32, 1)
 			constexpr uint32_t idesc64 = make_idesc_f16_f32(128, 64, false, false);
 			constexpr uint32_t idesc16 = make_idesc_f16_f32(128, 16, false, false);
 			const uint32_t w_addr = smem_u32(w_sm), ring_addr = smem_u32(ring);
-			uint32_t a_cnt[NT];
-#pragma unroll
-			for (int s = 0; s < NT; ++s)
-				a_cnt[s] = 0;
+			uint32_t a_par = 0; // bit s = parity of the next a_full[s] phase to wait for
 			mbar_wait(w_full, 0);
 			for (uint32_t r = 0; r * NT < my_tiles; ++r) {
 #pragma unroll 1
@@ -147,13 +144,13 @@ __global__ void __launch_bounds__((NT * 4 + 2) * 32, 1)
 						const uint32_t st = j % kStages;
 						if (IN_MODE == NRC_IN_ENCODED && l == 0) {
 							if (r > 0) { // accumulator of this slot drained by the previous tile's last epilogue
-								mbar_wait(a_full + s, a_cnt[s] & 1);
-								++a_cnt[s];
+								mbar_wait(a_full + s, (a_par >> s) & 1);
+								a_par ^= 1u << s;
 							}
 							mbar_wait(in_full + st, (j / kStages) & 1);
 						} else {
-							mbar_wait(a_full + s, a_cnt[s] & 1);
-							++a_cnt[s];
+							mbar_wait(a_full + s, (a_par >> s) & 1);
+							a_par ^= 1u << s;
 						}
 						tc_fence_after();
 						const uint32_t b_addr = w_addr + l * 8192;
@@ -211,8 +208,7 @@ __global__ void __launch_bounds__((NT * 4 + 2) * 32, 1)
 				}
 				tmem_st_x32(a_t, o);
 				tc_wait_st();
-				tc_fence_before();
-				mbar_arrive(a_full + s);
+				warp_arrive_after_tcgen05(a_full + s);
 			}
 #pragma unroll 1
 			for (int l = 0; l < NRC_HIDDEN_LAYERS; ++l) {
@@ -232,8 +228,7 @@ __global__ void __launch_bounds__((NT * 4 + 2) * 32, 1)
 					o[16 + i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
 				tmem_st_x32(a_t, o);
 				tc_wait_st();
-				tc_fence_before();
-				mbar_arrive(a_full + s);
+				warp_arrive_after_tcgen05(a_full + s);
 			}
 			mbar_wait(d_full + s, d_cnt & 1);
 			++d_cnt;
@@ -241,10 +236,8 @@ __global__ void __launch_bounds__((NT * 4 + 2) * 32, 1)
 			uint32_t y[4];
 			tmem_ld_x4(d_t, y);
 			tc_wait_ld();
-			if (IN_MODE == NRC_IN_ENCODED) {
-				tc_fence_before();
-				mbar_arrive(a_full + s);
-			}
+			if (IN_MODE == NRC_IN_ENCODED)
+				warp_arrive_after_tcgen05(a_full + s);
 			if (valid)
 				write_result(p, gi, __uint_as_float(y[0]), __uint_as_float(y[1]), __uint_as_float(y[2]));
 		}

@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(kGradThreads, 1)
 	const uint32_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
 	if (threadIdx.x == 0) {
-		mbar_init(w_full, 1), mbar_init(in_full, 1), mbar_init(a_full, 128), mbar_init(d_full, 1), mbar_init(tile_done, 1);
+		mbar_init(w_full, 1), mbar_init(in_full, 1), mbar_init(a_full, 4), mbar_init(d_full, 1), mbar_init(tile_done, 1);
 		fence_mbar_init();
 	}
 	if (warp == 4)
@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(kGradThreads, 1)
 				}
 				store_row_sw128(act_sm, row, o);
 				fence_proxy_async_smem();
-				mbar_arrive(a_full);
+				warp_arrive_after_tcgen05(a_full);
 			}
 			if (valid && IN_MODE != NRC_IN_IMAGE_RANDOM) {
 				if (p.target_is_f16) {
@@ -247,8 +247,7 @@ __global__ void __launch_bounds__(kGradThreads, 1)
 					o[i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
 				store_row_sw128(act_sm + (l + 1) * 16384, row, o);
 				fence_proxy_async_smem();
-				tc_fence_before();
-				mbar_arrive(a_full);
+				warp_arrive_after_tcgen05(a_full);
 			}
 			// ---- output layer + loss gradient (NN_nv.glsl:148-196)
 			{
@@ -286,8 +285,7 @@ __global__ void __launch_bounds__(kGradThreads, 1)
 				*(uint4 *)(r + ((0 ^ (row & 7)) << 4)) = make_uint4(cvt_pack_f16x2(g[0], g[1]), cvt_pack_f16x2(g[2], 0.0f), 0u, 0u);
 				*(uint4 *)(r + ((1 ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
 				fence_proxy_async_smem();
-				tc_fence_before();
-				mbar_arrive(a_full);
+				warp_arrive_after_tcgen05(a_full);
 			}
 			// ---- backward epilogues: delta_{l-1} = fp16(D) * [a_l > 0], NaN -> 0 (NN_nv.glsl:198-220, 240-242)
 #pragma unroll 1
@@ -308,8 +306,7 @@ __global__ void __launch_bounds__(kGradThreads, 1)
 				}
 				store_row_sw128(delta_sm + ((5 - (l - 1)) & 1) * 16384, row, o);
 				fence_proxy_async_smem();
-				tc_fence_before();
-				mbar_arrive(a_full);
+				warp_arrive_after_tcgen05(a_full);
 			}
 		}
 		// ---- all tiles issued: drain the dW accumulators (M=64 TMEM layout: row r -> lane (r%16) + 32*(r/16))

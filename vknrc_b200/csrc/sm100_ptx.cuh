@@ -25,6 +25,14 @@ __device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
 	asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival per warp: every lane orders its own tcgen05 traffic, the warp converges, lane 0 signals.
+// (128 per-thread arrivals on one mbarrier serialise in the LSU; 4 per tile do not.)
+__device__ __forceinline__ void warp_arrive_after_tcgen05(uint64_t *bar) {
+	asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+	__syncwarp();
+	if ((threadIdx.x & 31u) == 0)
+		mbar_arrive(bar);
+}
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
@@ -41,6 +49,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
 #define SM100_MBAR_SPIN_LIMIT (1u << 24)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+	if (mbar_try_wait(bar, parity))
+		return;
+#pragma unroll 1 // never unroll: an unrolled spin loop bloats the kernel far past the instruction cache
 	for (uint32_t i = 0; i < SM100_MBAR_SPIN_LIMIT; ++i)
 		if (mbar_try_wait(bar, parity))
 			return;
