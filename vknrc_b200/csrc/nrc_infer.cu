@@ -5,17 +5,36 @@
 //   * warp TMA  : stages all six weight matrices once (TMA tensor loads with the 128-byte swizzle straight from the
 //                 reference's row-major fp16 buffer; rows past 323 are zero-filled by TMA, which pads W5 from 3 to 64
 //                 rows for free) and, for pre-encoded inputs, streams 128x64 fp16 input tiles through a smem ring;
-//   * warp MMA  : one elected thread issues tcgen05.mma for NT tiles in flight ("slots"). Layer l of a slot is
-//                 D[128 samples x 64] (fp32, TMEM) = A_l (fp16, TMEM, except pre-encoded layer 0 from smem) x W_l^T;
-//   * 4 warps per slot: epilogue. Thread = sample = TMEM lane: tcgen05.ld the accumulator row, ReLU + fp32->fp16 in
-//                 one cvt.rn.relu.f16x2.f32 per pair, tcgen05.st it back as the next layer's A operand. Activations
-//                 never leave TMEM. For record inputs the same threads run the input encoding and write A_0 directly.
-// Hand-offs are mbarriers: a_full[slot] (epilogue -> MMA: operand ready, accumulator drained), d_full[slot]
-// (tcgen05.commit -> epilogue), in_full/in_empty[stage] (TMA <-> MMA).
+//   * NT "slots" of 4 warps, each owning one 128-sample tile in flight (64 accumulator + 32 operand TMEM columns).
+//                 Layer l of a slot is D[128 samples x 64] (fp32, TMEM) = A_l (fp16, TMEM; pre-encoded layer 0 from the
+//                 smem ring) x W_l^T, issued as 4 tcgen05.mma (K=16) by one elected thread of the slot's first warp.
+//                 Epilogue: thread = sample = TMEM lane: tcgen05.ld the accumulator row, ReLU + fp32->fp16 in one
+//                 cvt.rn.relu.f16x2.f32 per pair, tcgen05.st it back as the next layer's A operand. Activations never
+//                 leave TMEM. For record inputs the same threads run the input encoding and write A_0 directly.
+// Hand-offs: a 128-thread named barrier inside the slot (operand stored / accumulator drained -> issuer), the
+// mbarrier d_full[slot] (tcgen05.commit -> epilogue) and in_full/in_empty[stage] (TMA <-> layer-0 MMA).
 #include "nrc_kernels.h"
 #include "nrc_encode.cuh"
 
 using namespace sm100;
+
+#ifdef NRC_TRACE
+// development aid: CTA 0 records (tag, clock) pairs; tag = who<<24 | layer<<16 | tile
+__device__ unsigned long long g_nrc_trace[4][4096];
+__device__ unsigned int g_nrc_trace_n[4];
+#define NRC_TRACE_EV(who, tag)                                                                                         \
+	do {                                                                                                               \
+		if (blockIdx.x == 0) {                                                                                         \
+			unsigned int i_ = g_nrc_trace_n[who]++;                                                                    \
+			if (i_ < 2048) {                                                                                           \
+				g_nrc_trace[who][2 * i_] = (tag);                                                                      \
+				g_nrc_trace[who][2 * i_ + 1] = clock64();                                                              \
+			}                                                                                                          \
+		}                                                                                                              \
+	} while (0)
+#else
+#define NRC_TRACE_EV(who, tag)
+#endif
 
 namespace nrc {
 
@@ -66,18 +85,18 @@ __device__ __forceinline__ void write_result(const InferParams &p, uint64_t gi, 
 }
 
 template <int NT, int IN_MODE>
-__global__ void __launch_bounds__((NT * 4 + 2) * 32, 1)
+__global__ void __launch_bounds__((NT * 4 + 1) * 32, 1)
     nrc_infer_kernel(const InferParams p, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_in) {
 	using L = InferSmem<NT>;
 	constexpr int kStages = L::kStages;
-	constexpr uint32_t TMA_WARP = NT * 4, MMA_WARP = NT * 4 + 1;
+	constexpr uint32_t TMA_WARP = NT * 4;
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	uint8_t *w_sm = smem;
 	uint8_t *ring = smem + L::kRingOff;
 	uint64_t *bars = (uint64_t *)(smem + L::kBarOff);
-	uint64_t *w_full = bars, *in_full = bars + 1, *in_empty = in_full + kStages, *d_full = in_empty + kStages, *a_full = d_full + NT;
-	uint32_t *tmem_slot = (uint32_t *)(a_full + NT);
+	uint64_t *w_full = bars, *in_full = bars + 1, *in_empty = in_full + kStages, *d_full = in_empty + kStages;
+	uint32_t *tmem_slot = (uint32_t *)(d_full + NT);
 
 	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 	uint64_t n = p.n;
@@ -95,7 +114,7 @@ __global__ void __launch_bounds__((NT * 4 + 2) * 32, 1)
 		for (int i = 0; i < kStages; ++i)
 			mbar_init(in_full + i, 1), mbar_init(in_empty + i, 1);
 		for (int i = 0; i < NT; ++i)
-			mbar_init(d_full + i, 1), mbar_init(a_full + i, 4);
+			mbar_init(d_full + i, 1);
 		fence_mbar_init();
 	}
 	if (warp == TMA_WARP)
@@ -124,63 +143,24 @@ __global__ void __launch_bounds__((NT * 4 + 2) * 32, 1)
 			}
 		}
 		__syncwarp();
-	} else if (warp == MMA_WARP) {
-		// ------------------------------------------------------------------------------------------ MMA issuer
-		if (elect_one()) {
-			constexpr uint32_t idesc64 = make_idesc_f16_f32(128, 64, false, false);
-			constexpr uint32_t idesc16 = make_idesc_f16_f32(128, 16, false, false);
-			const uint32_t w_addr = smem_u32(w_sm), ring_addr = smem_u32(ring);
-			uint32_t a_par = 0; // bit s = parity of the next a_full[s] phase to wait for
-			mbar_wait(w_full, 0);
-			for (uint32_t r = 0; r * NT < my_tiles; ++r) {
-#pragma unroll 1
-				for (int l = 0; l < NRC_LAYERS; ++l) {
-#pragma unroll
-					for (int s = 0; s < NT; ++s) {
-						const uint32_t j = r * NT + s;
-						if (j >= my_tiles)
-							continue;
-						const uint32_t d_t = tmem + s * 96, a_t = d_t + 64;
-						const uint32_t st = j % kStages;
-						if (IN_MODE == NRC_IN_ENCODED && l == 0) {
-							if (r > 0) { // accumulator of this slot drained by the previous tile's last epilogue
-								mbar_wait(a_full + s, (a_par >> s) & 1);
-								a_par ^= 1u << s;
-							}
-							mbar_wait(in_full + st, (j / kStages) & 1);
-						} else {
-							mbar_wait(a_full + s, (a_par >> s) & 1);
-							a_par ^= 1u << s;
-						}
-						tc_fence_after();
-						const uint32_t b_addr = w_addr + l * 8192;
-						if (IN_MODE == NRC_IN_ENCODED && l == 0) {
-							const uint32_t a_addr = ring_addr + st * 16384;
-#pragma unroll
-							for (int k = 0; k < 4; ++k)
-								mma_ss(d_t, make_smem_desc_sw128(a_addr + k * 32, 0, 1024), make_smem_desc_sw128(b_addr + k * 32, 0, 1024),
-								       idesc64, k > 0);
-							tc_commit(in_empty + st);
-						} else if (l < NRC_HIDDEN_LAYERS) {
-#pragma unroll
-							for (int k = 0; k < 4; ++k)
-								mma_ts(d_t, a_t + k * 8, make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc64, k > 0);
-						} else {
-#pragma unroll
-							for (int k = 0; k < 4; ++k)
-								mma_ts(d_t, a_t + k * 8, make_smem_desc_sw128(b_addr + k * 32, 0, 1024), idesc16, k > 0);
-						}
-						tc_commit(d_full + s);
-					}
-				}
-			}
-		}
-		__syncwarp();
 	} else {
-		// ------------------------------------------------------------------------------------------ epilogue warps
+		// ------------------------------------------------------------------------------------------ slot warpgroups
+		// Each slot is self-contained: its 128 threads run the epilogues and one elected thread of its first warp issues
+		// the slot's own tcgen05.mma. A dedicated issuer thread for all slots serialises ~300 cycles of issue + wait
+		// latency per layer-step (measured) and starves the tensor pipe; NT issuers in parallel do not.
 		const uint32_t s = warp >> 2, q = warp & 3, row = q * 32 + lane;
-		const uint32_t d_t = tmem_addr(tmem, q * 32, s * 96), a_t = d_t + 64;
+		const uint32_t d_col = tmem + s * 96, a_col = d_col + 64;                        // issuer view (lane 0)
+		const uint32_t d_t = tmem_addr(tmem, q * 32, s * 96), a_t = d_t + 64;            // this warp's 32 lanes
+		const uint32_t w_addr = smem_u32(w_sm), ring_addr = smem_u32(ring);
+		constexpr uint32_t idesc64 = make_idesc_f16_f32(128, 64, false, false);
+		constexpr uint32_t idesc16 = make_idesc_f16_f32(128, 16, false, false);
+		auto slot_sync = [&]() { // all of this slot's TMEM traffic is complete and visible to the issuer
+			tc_fence_before();
+			asm volatile("bar.sync %0, 128;" ::"r"(s + 1) : "memory");
+		};
 		uint32_t d_cnt = 0;
+		if (q == 0)
+			mbar_wait(w_full, 0);
 		for (uint32_t j = s; j < my_tiles; j += NT) {
 			const uint32_t tile = blockIdx.x + j * gridDim.x;
 			const uint64_t gi = (uint64_t)tile * NRC_TILE + row;
@@ -208,38 +188,63 @@ __global__ void __launch_bounds__((NT * 4 + 2) * 32, 1)
 				}
 				tmem_st_x32(a_t, o);
 				tc_wait_st();
-				warp_arrive_after_tcgen05(a_full + s);
+				slot_sync();
 			}
 #pragma unroll 1
-			for (int l = 0; l < NRC_HIDDEN_LAYERS; ++l) {
+			for (int l = 0; l < NRC_LAYERS; ++l) {
+				// ---- issue layer l of this slot's tile
+				if (q == 0) {
+					if (elect_one()) {
+						tc_fence_after();
+						const uint32_t b_addr = w_addr + l * 8192;
+						if (IN_MODE == NRC_IN_ENCODED && l == 0) {
+							const uint32_t st = j % kStages;
+							mbar_wait(in_full + st, (j / kStages) & 1);
+							const uint32_t a_addr = ring_addr + st * 16384;
+#pragma unroll
+							for (int k = 0; k < 4; ++k)
+								mma_ss(d_col, make_smem_desc_sw128(a_addr + k * 32, 0, 1024), make_smem_desc_sw128(b_addr + k * 32, 0, 1024),
+								       idesc64, k > 0);
+							tc_commit(in_empty + st);
+						} else {
+#pragma unroll
+							for (int k = 0; k < 4; ++k)
+								mma_ts(d_col, a_col + k * 8, make_smem_desc_sw128(b_addr + k * 32, 0, 1024), l < NRC_HIDDEN_LAYERS ? idesc64 : idesc16,
+								       k > 0);
+						}
+						tc_commit(d_full + s);
+					}
+					__syncwarp();
+				}
+				// ---- epilogue of layer l
 				mbar_wait(d_full + s, d_cnt & 1);
 				++d_cnt;
 				tc_fence_after();
-				uint32_t v[32], o[32];
-				tmem_ld_x32(d_t, v);
-				tc_wait_ld();
+				if (l < NRC_HIDDEN_LAYERS) {
+					uint32_t v[32], o[32];
+					tmem_ld_x32(d_t, v);
+					tc_wait_ld();
 #pragma unroll
-				for (int i = 0; i < 16; ++i)
-					o[i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-				tmem_ld_x32(d_t + 32, v);
-				tc_wait_ld();
+					for (int i = 0; i < 16; ++i)
+						o[i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+					tmem_ld_x32(d_t + 32, v);
+					tc_wait_ld();
 #pragma unroll
-				for (int i = 0; i < 16; ++i)
-					o[16 + i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-				tmem_st_x32(a_t, o);
-				tc_wait_st();
-				warp_arrive_after_tcgen05(a_full + s);
+					for (int i = 0; i < 16; ++i)
+						o[16 + i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+					tmem_st_x32(a_t, o);
+					tc_wait_st();
+					slot_sync();
+				} else {
+					uint32_t y[4];
+					tmem_ld_x4(d_t, y);
+					tc_wait_ld();
+					if (IN_MODE == NRC_IN_ENCODED)
+						slot_sync(); // accumulator drained before the next tile's layer 0 overwrites it
+					if (valid)
+						write_result(p, gi, __uint_as_float(y[0]), __uint_as_float(y[1]), __uint_as_float(y[2]));
+				}
 			}
-			mbar_wait(d_full + s, d_cnt & 1);
-			++d_cnt;
-			tc_fence_after();
-			uint32_t y[4];
-			tmem_ld_x4(d_t, y);
-			tc_wait_ld();
-			if (IN_MODE == NRC_IN_ENCODED)
-				warp_arrive_after_tcgen05(a_full + s);
-			if (valid)
-				write_result(p, gi, __uint_as_float(y[0]), __uint_as_float(y[1]), __uint_as_float(y[2]));
 		}
 	}
 	tc_fence_before();
@@ -259,7 +264,7 @@ template <int NT, int IN_MODE> static cudaError_t launch(const InferParams &p, c
 	}
 	const uint64_t ntiles = (p.n + NRC_TILE - 1) / NRC_TILE;
 	const uint32_t grid = (uint32_t)(ntiles < (uint64_t)sms ? ntiles : (uint64_t)sms);
-	kern<<<grid, (NT * 4 + 2) * 32, InferSmem<NT>::kBytes, stream>>>(p, tm_w, tm_in);
+	kern<<<grid, (NT * 4 + 1) * 32, InferSmem<NT>::kBytes, stream>>>(p, tm_w, tm_in);
 	return cudaGetLastError();
 }
 
