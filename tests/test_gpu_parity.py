@@ -283,6 +283,30 @@ def test_gradient_unpacked_and_adam_match_oracle(nrc, oracle_mod, state):
             opt.state.t, opt.state.beta1_t, opt.state.beta2_t, opt.state.alpha_t, opt.state.alpha_t_1)
 
 
+def test_fused_train_batch_equals_split_path(nrc, state):
+    """nrc_train_batch_unpacked (gradient + ONE reduce-and-Adam kernel) must equal nrc_gradient_unpacked followed by
+    nrc_adam_step (the multi-GPU path, with the all-reduce in between) bit for bit."""
+    w32 = he_weights(63)
+    rec, tgt = dev(random_records(14, 5000)), torch.rand((5000, 3), device="cuda")
+    results = []
+    for fused in (True, False):
+        state.set_weights(w32)
+        state.set_use_ema_weights(True)
+        for step in range(3):
+            if fused:
+                state.train_batch_unpacked(rec, tgt, write_use_weights=(step == 2))
+            else:
+                state.gradient_unpacked(rec, tgt)
+                state.adam_step(write_use_weights=(step == 2))
+        results.append(state.download())
+    a, b = results
+    assert np.array_equal(a["optimizer_entries"].view(np.uint32), b["optimizer_entries"].view(np.uint32))
+    assert np.array_equal(a["weights"].view(np.uint16), b["weights"].view(np.uint16))
+    assert np.array_equal(a["use_weights"].view(np.uint16), b["use_weights"].view(np.uint16))
+    assert a["optimizer_state"] == b["optimizer_state"] and a["optimizer_state"]["t"] == 3
+    assert np.array_equal(a["gradients"], b["gradients"])
+
+
 def test_empty_and_overfull_batches(nrc, oracle_mod, state):
     w32 = he_weights(71)
     state.set_weights(w32)

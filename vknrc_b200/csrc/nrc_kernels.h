@@ -60,18 +60,6 @@ struct GradParams {
 	void *y_out;             // optional [n][3] fp32 predictions (unclamped), for loss-curve checks
 };
 
-struct ReduceParams {
-	const float *partials;
-	uint32_t num_partials;
-	float *gradients;      // [NRC_GRAD_STRIDE]
-	int accumulate;        // 1: gradients += sum (test/train_NV.comp semantics), 0: gradients = sum
-	uint32_t limit;        // number of leading elements to produce (20672 for a caller's dW, NRC_GRAD_STRIDE otherwise)
-	// fused nrc_train_prepare.comp:16-28 (done by one thread; all optional)
-	uint32_t *d_count;     // clamped in place to batch_cap
-	uint32_t batch_cap;
-	NrcOptimizerState *opt_state;
-};
-
 struct AdamParams {
 	const float *gradients;          // [NRC_GRAD_STRIDE]; the divisor is gradients[NRC_GRAD_COUNT_SLOT]
 	NrcOptimizerEntry *entries;
@@ -80,6 +68,18 @@ struct AdamParams {
 	__half *weights;                 // fp16, reference layout
 	__half *use_weights;             // nullptr = the non-WRITE_USE_WEIGHTS variant
 	int use_ema;
+};
+
+struct ReduceParams {
+	const float *partials;
+	uint32_t num_partials;
+	float *gradients;      // [NRC_GRAD_STRIDE]
+	int accumulate;        // 1: gradients += sum (test/train_NV.comp semantics), 0: gradients = sum
+	uint32_t limit;        // number of leading elements to produce (20672 for a caller's dW, NRC_GRAD_STRIDE otherwise)
+	uint32_t *d_count;     // optional: clamped in place to batch_cap (nrc_train_prepare.comp:17-19)
+	uint32_t batch_cap;
+	int fuse_adam;         // 1: also run the optimizer step on the reduced gradient (single-GPU path, saves a launch)
+	AdamParams adam;
 };
 
 struct SgdParams { // mlp_learning_an_image/optimize.comp:21-29

@@ -196,7 +196,7 @@ int NrcState::Infer(InferParams p, const void *encoded_inputs, const __half *wei
 }
 
 int NrcState::Gradient(GradParams p, const void *encoded_inputs, const __half *weights, float *gradients, bool accumulate, uint32_t *d_count,
-                       uint32_t batch_cap, cudaStream_t stream) {
+                       uint32_t batch_cap, cudaStream_t stream, int fused_step) {
 	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
 	CUtensorMap tm_w, tm_in;
 	std::string err;
@@ -214,6 +214,12 @@ int NrcState::Gradient(GradParams p, const void *encoded_inputs, const __half *w
 	r.partials = m_partials, r.num_partials = num_partials, r.gradients = gradients, r.accumulate = accumulate ? 1 : 0;
 	r.limit = accumulate ? NRC_WEIGHT_COUNT : NRC_GRAD_STRIDE;
 	r.d_count = d_count, r.batch_cap = batch_cap;
+	if (fused_step) {
+		r.fuse_adam = 1;
+		r.adam.gradients = gradients, r.adam.entries = m_optimizer_entries, r.adam.opt_state = m_optimizer_state;
+		r.adam.done_counter = m_done_counter, r.adam.weights = m_weights;
+		r.adam.use_weights = fused_step == 2 ? m_use_weights : nullptr, r.adam.use_ema = m_use_ema_weights ? 1 : 0;
+	}
 	NRC_CUDA_TRY(launch_reduce(r, stream), sink);
 	return NRC_OK;
 }
@@ -408,8 +414,8 @@ int nrc_infer_scatter_unpacked(nrc_handle_t h, const uint32_t *d_dst, uint32_t d
 	return h->state.Infer(p, nullptr, h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
 }
 
-int nrc_gradient_unpacked(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets, uint32_t target_stride,
-                          uint32_t *d_count, uint32_t max_count, void *stream) {
+static int gradient_unpacked_impl(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets, uint32_t target_stride,
+                                  uint32_t *d_count, uint32_t max_count, void *stream, int fused_step) {
 	NRC_REQUIRE(h, "null handle");
 	NRC_REQUIRE(max_count == 0 || (d_inputs && d_targets), "nrc_gradient_unpacked: null buffer");
 	NRC_REQUIRE(input_stride >= 56 && input_stride % 8 == 0 && ((uintptr_t)d_inputs & 7u) == 0, "nrc_gradient_unpacked: inputs must be 8-byte aligned, stride >= 56 and a multiple of 8");
@@ -418,7 +424,13 @@ int nrc_gradient_unpacked(nrc_handle_t h, const void *d_inputs, uint32_t input_s
 	p.n = max_count, p.in_mode = NRC_IN_UNPACKED, p.loss_kind = NRC_LOSS_RELATIVE_L2_LUMINANCE, p.loss_scale = NRC_LOSS_SCALE;
 	p.in = d_inputs, p.in_stride_bytes = input_stride, p.target = d_targets, p.target_stride_bytes = target_stride, p.target_is_f16 = 0;
 	p.y_out = h->state.GetPredictionCapture();
-	return h->state.Gradient(p, nullptr, h->state.GetWeightBuffer(), h->state.GetGradientBuffer(), false, d_count, max_count, (cudaStream_t)stream);
+	return h->state.Gradient(p, nullptr, h->state.GetWeightBuffer(), h->state.GetGradientBuffer(), false, d_count, max_count, (cudaStream_t)stream,
+	                         fused_step);
+}
+
+int nrc_gradient_unpacked(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets, uint32_t target_stride,
+                          uint32_t *d_count, uint32_t max_count, void *stream) {
+	return gradient_unpacked_impl(h, d_inputs, input_stride, d_targets, target_stride, d_count, max_count, stream, 0);
 }
 
 int nrc_gradient_encoded(nrc_handle_t h, const void *d_inputs, const void *d_targets, uint32_t *d_count, uint32_t max_count, int relative_loss,
@@ -437,12 +449,10 @@ int nrc_adam_step(nrc_handle_t h, int write_use_weights, void *stream) {
 	return h->state.AdamStep(write_use_weights != 0, (cudaStream_t)stream);
 }
 
+// gradient kernel + ONE kernel that reduces the partials deterministically and applies Adam/EMA (2 launches per batch)
 int nrc_train_batch_unpacked(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets, uint32_t target_stride,
                              uint32_t *d_count, uint32_t max_count, int write_use_weights, void *stream) {
-	int rc = nrc_gradient_unpacked(h, d_inputs, input_stride, d_targets, target_stride, d_count, max_count, stream);
-	if (rc != NRC_OK)
-		return rc;
-	return nrc_adam_step(h, write_use_weights, stream);
+	return gradient_unpacked_impl(h, d_inputs, input_stride, d_targets, target_stride, d_count, max_count, stream, write_use_weights ? 2 : 1);
 }
 
 int nrc_image_train_step(nrc_handle_t h, const void *d_image_rgba8, uint32_t image_w, uint32_t image_h, uint32_t seed_x, uint32_t seed_y,

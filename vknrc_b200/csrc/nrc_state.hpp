@@ -66,8 +66,10 @@ public:
 
 	// ---- hot path
 	int Infer(InferParams p, const void *encoded_inputs, const __half *weights, cudaStream_t stream);
+	// fused_step: 0 = gradient + reduction only; 1 / 2 = also the Adam step inside the reduction kernel
+	// (2 = write use_weights as well)
 	int Gradient(GradParams p, const void *encoded_inputs, const __half *weights, float *gradients, bool accumulate, uint32_t *d_count,
-	             uint32_t batch_cap, cudaStream_t stream);
+	             uint32_t batch_cap, cudaStream_t stream, int fused_step = 0);
 	int AdamStep(bool write_use_weights, cudaStream_t stream);
 	int SgdStep(float lr, float batch, cudaStream_t stream);
 	void SetPredictionCapture(float *d) { m_prediction_capture = d; }
