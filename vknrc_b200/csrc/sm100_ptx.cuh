@@ -36,17 +36,18 @@ __device__ __forceinline__ void warp_arrive_after_tcgen05(uint64_t *bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
 	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity) {
+// try_wait suspends the thread in hardware until the phase completes or `hint_ns` elapses (a hint, system-dependent).
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity, uint32_t hint_ns = 20000u) {
 	uint32_t ok;
-	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+	asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\tselp.u32 %0, 1, 0, p;\n\t}"
 	             : "=r"(ok)
-	             : "r"(smem_u32(bar)), "r"(parity)
+	             : "r"(smem_u32(bar)), "r"(parity), "r"(hint_ns)
 	             : "memory");
 	return ok != 0;
 }
 // Bounded wait: a protocol bug traps (reported by the C-ABI as a launch failure) instead of hanging the GPU.
 #ifndef SM100_MBAR_SPIN_LIMIT
-#define SM100_MBAR_SPIN_LIMIT (1u << 24)
+#define SM100_MBAR_SPIN_LIMIT (1u << 22)
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 	if (mbar_try_wait(bar, parity))
@@ -151,6 +152,15 @@ __device__ __forceinline__ void tmem_ld_x64(uint32_t taddr, uint32_t *v) {
 	             : "r"(taddr)
 	             : "memory");
 }
+// 64 consecutive columns holding 16-bit data (e.g. fp16 accumulators, one per 32-bit cell) -> 32 registers of packed pairs
+__device__ __forceinline__ void tmem_ld_x32_pack16(uint32_t taddr, uint32_t *v) {
+	asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.pack::16b.b32 "
+	             "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+	             "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+	             : SM100_R16(v, 0), SM100_R16(v, 16)
+	             : "r"(taddr)
+	             : "memory");
+}
 #define SM100_I4(v, o) "r"(v[o]), "r"(v[o + 1]), "r"(v[o + 2]), "r"(v[o + 3])
 #define SM100_I16(v, o) SM100_I4(v, o), SM100_I4(v, o + 4), SM100_I4(v, o + 8), SM100_I4(v, o + 12)
 __device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t *v) {
@@ -178,6 +188,17 @@ __device__ __forceinline__ void tmem_st_x32(uint32_t taddr, const uint32_t *v) {
 //   [16] B major (1 = MN) | [17,23) N >> 3 | [24,29) M >> 4
 __host__ __device__ constexpr uint32_t make_idesc_f16_f32(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major) {
 	return (1u << 4) | ((a_mn_major ? 1u : 0u) << 15) | ((b_mn_major ? 1u : 0u) << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+// same with fp16 D (accumulators rounded to fp16 after every K=16 instruction, one per 32-bit TMEM cell)
+__host__ __device__ constexpr uint32_t make_idesc_f16_f16(uint32_t M, uint32_t N, bool a_mn_major, bool b_mn_major) {
+	return make_idesc_f16_f32(M, N, a_mn_major, b_mn_major) & ~(3u << 4);
+}
+// relu on a packed pair of fp16 (HFMA2.RELU: fma pipe)
+__device__ __forceinline__ uint32_t relu_f16x2(uint32_t x) {
+	uint32_t r;
+	asm("fma.rn.relu.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(x), "r"(0x3c003c00u), "r"(0x80008000u));
+	return r;
 }
 
 // Shared-memory matrix descriptor, 128-byte swizzle. Every operand tile in this project is an array of 128-byte rows
