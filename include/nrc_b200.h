@@ -104,7 +104,8 @@ int nrc_infer_scatter_unpacked(nrc_handle_t h, const uint32_t *d_dst, uint32_t d
  * nrc_adam_step: nrc_train_prepare.comp:22-28 + nrc_optimize.comp:32-54 using gradient[20673] as the record count
  *   (so that a multi-GPU caller can all-reduce the gradient buffer in between); writes `weights`, and `use_weights`
  *   iff write_use_weights (the reference does that for the frame's last batch only, NRCRenderGraph.cpp:66-68).
- * nrc_train_batch_unpacked = both, back to back. */
+ * nrc_train_batch_unpacked = both in ONE kernel launch (the optimizer runs on the reduced gradient inside the same
+ *   cooperative kernel). */
 int nrc_gradient_unpacked(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets,
                           uint32_t target_stride, uint32_t *d_count, uint32_t max_count, void *stream);
 int nrc_gradient_encoded(nrc_handle_t h, const void *d_inputs, const void *d_targets_f16vec3, uint32_t *d_count,
@@ -113,6 +114,11 @@ int nrc_adam_step(nrc_handle_t h, int write_use_weights, void *stream);
 int nrc_train_batch_unpacked(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets,
                              uint32_t target_stride, uint32_t *d_count, uint32_t max_count, int write_use_weights,
                              void *stream);
+/* nrc_train_frame_unpacked = the whole NNTrain schedule of one frame (src/rg/NRCRenderGraph.cpp:57-70): four dependent
+ *   batches, each clear -> prepare -> gradient -> optimize, use_weights written by the last one, in ONE kernel launch. */
+int nrc_train_frame_unpacked(nrc_handle_t h, const void *const d_inputs[4], uint32_t input_stride,
+                             const void *const d_targets[4], uint32_t target_stride, uint32_t *const d_counts[4],
+                             uint32_t max_count, void *stream);
 /* optional fp32 [max_count][3] buffer that receives the (unclamped) training predictions of the next gradient call */
 void nrc_set_prediction_capture(nrc_handle_t h, float *d_predictions);
 

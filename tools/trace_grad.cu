@@ -1,0 +1,49 @@
+// trace_grad.cu -- development tool: runs nrc_gradient_kernel built with -DNRC_TRACE on one 16384-record batch and
+// prints CTA 0 / thread 0's event timeline (tags: 1 entry, 2 setup done, 3 inputs ready, 0x1l fwd accumulator l ready,
+// 0x2l fwd epilogue l stored, 0x3l dA accumulator ready, 0x4l delta stored, 5 tile loop done, 6 dW complete, 7 dW
+// staged, 8 partial written, 9 grid barrier passed, 10 exit).
+#include "../vknrc_b200/csrc/nrc_train.cu"
+#include <cstdio>
+typedef CUresult (*PFN)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                        const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static void mk(CUtensorMap *tm, void *base, uint64_t rows, uint32_t box) {
+	void *p; cudaDriverEntryPointQueryResult q;
+	cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q);
+	cuuint64_t gd[2] = {64, rows}, gs[1] = {128}; cuuint32_t bx[2] = {64, box}, es[2] = {1, 1};
+	((PFN)p)(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, base, gd, gs, bx, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+	         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+}
+int main(int argc, char **argv) {
+	const uint64_t n = argc > 1 ? strtoull(argv[1], 0, 10) : 16384;
+	__half *w; float *rec, *tgt, *partials;
+	cudaMalloc(&w, 6 * 8192); cudaMalloc(&rec, n * 56); cudaMalloc(&tgt, n * 12); cudaMalloc(&partials, 148 * NRC_GRAD_STRIDE * 4);
+	cudaMemset(w, 0, 6 * 8192); cudaMemset(rec, 0x11, n * 56); cudaMemset(tgt, 0, n * 12);
+	CUtensorMap tw; mk(&tw, w, 323, 64);
+	const int nb = argc > 2 ? atoi(argv[2]) : 1; // batches per launch (frame = 4)
+	NrcOptimizerEntry *entries; NrcOptimizerState *ost; uint32_t *sync; float *grads; __half *uw;
+	cudaMalloc(&entries, 20672 * 16); cudaMalloc(&ost, 20); cudaMalloc(&sync, 16); cudaMalloc(&grads, NRC_GRAD_STRIDE * 4); cudaMalloc(&uw, 6 * 8192);
+	cudaMemset(entries, 0, 20672 * 16); cudaMemset(sync, 0, 16);
+	const NrcOptimizerState st0{0u, 1.0f, 1.0f, 1.0f, 0.0f}; cudaMemcpy(ost, &st0, 20, cudaMemcpyHostToDevice);
+	nrc::TrainParams tp{};
+	for (int b = 0; b < nb; ++b) {
+		nrc::GradParams &p = tp.batch[b];
+		p.n = n; p.in_mode = nrc::NRC_IN_UNPACKED; p.loss_kind = nrc::NRC_LOSS_RELATIVE_L2_LUMINANCE; p.loss_scale = 1.0f;
+		p.in = rec; p.in_stride_bytes = 56; p.target = tgt; p.target_stride_bytes = 12; p.partials = partials;
+		tp.adam_mode[b] = b == nb - 1 ? 2 : 1;
+	}
+	tp.num_batches = nb; tp.gradients = grads; tp.limit = NRC_GRAD_STRIDE; tp.batch_cap = (uint32_t)n; tp.grid_bar = sync + 2;
+	tp.adam.gradients = grads; tp.adam.entries = entries; tp.adam.opt_state = ost; tp.adam.done_counter = sync; tp.adam.weights = w; tp.adam.use_weights = uw;
+	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+	for (int it = 0; it < 4; ++it) {
+		cudaEventRecord(e0);
+		cudaError_t le = nrc::launch_train(tp, tw, tw, 148, 0);
+		cudaEventRecord(e1);
+		cudaError_t e = cudaDeviceSynchronize();
+		float ms; cudaEventElapsedTime(&ms, e0, e1); printf("train kernel (%d batch%s of %llu) %.1f us (%s / %s)\n", nb, nb > 1 ? "es" : "", (unsigned long long)n, ms * 1e3, cudaGetErrorString(le), cudaGetErrorString(e));
+	}
+	static uint2 tr[NRC_GTRACE_CAP]; unsigned int cnt;
+	cudaMemcpyFromSymbol(tr, g_nrc_gtrace, sizeof(tr)); cudaMemcpyFromSymbol(&cnt, g_nrc_gtrace_n, sizeof(cnt));
+	for (unsigned i = 0; i < cnt; ++i)
+		printf("ev=0x%02x t=%u (+%u)\n", tr[i].x, tr[i].y - tr[0].y, i ? tr[i].y - tr[i - 1].y : 0);
+	return 0;
+}

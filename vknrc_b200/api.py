@@ -78,6 +78,8 @@ SIGNATURES = {
     "nrc_adam_step": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "nrc_train_batch_unpacked": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32,
                                            C.c_int, C.c_void_p]),
+    "nrc_train_frame_unpacked": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32,
+                                           C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p]),
     "nrc_set_prediction_capture": (None, [C.c_void_p, C.c_void_p]),
     "nrc_image_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.c_float, C.c_void_p]),
@@ -269,6 +271,14 @@ class NrcState:
         n = inputs.shape[0] if max_count is None else max_count
         _check(lib().nrc_train_batch_unpacked(self._h, _ptr(inputs), input_stride, _ptr(targets), target_stride, _ptr(count), n,
                                               int(write_use_weights), _stream()))
+
+    def train_frame_unpacked(self, inputs, targets, counts=None, max_count=None, input_stride=56, target_stride=12):
+        """inputs / targets / counts: sequences of 4 tensors (the frame's batches); ONE kernel launch."""
+        n = inputs[0].shape[0] if max_count is None else max_count
+        ins = (C.c_void_p * 4)(*[_ptr(t) for t in inputs])
+        tgs = (C.c_void_p * 4)(*[_ptr(t) for t in targets])
+        cns = (C.c_void_p * 4)(*[_ptr(t) for t in counts]) if counts is not None else None
+        _check(lib().nrc_train_frame_unpacked(self._h, ins, input_stride, tgs, target_stride, cns, n, _stream()))
 
     # ---- learn-an-image
     def image_train_step(self, image_rgba8, seed_x: int, seed_y: int, batch: int = 16384, lr: float = 0.01):

@@ -59,6 +59,47 @@ __device__ __forceinline__ void encode_nrc(const float in[14], uint32_t o[32]) {
 		o[i] = sm100::cvt_pack_f16x2(f[2 * i], f[2 * i + 1]);
 }
 
+// The same encoding split in two 32-feature halves (half 0 = features 0..31, half 1 = features 32..63), so that two
+// threads can share one record (the training kernel's epilogue warps each own 32 of a row's 64 columns).
+__device__ __forceinline__ void encode_nrc_half(const float in[14], uint32_t half, uint32_t o[16]) {
+	float f[32];
+	if (half == 0) {
+#pragma unroll
+		for (int k = 0; k < 12; ++k)
+			f[k] = tri((float)(1 << k) * in[0]), f[12 + k] = tri((float)(1 << k) * in[1]);
+#pragma unroll
+		for (int k = 0; k < 8; ++k)
+			f[24 + k] = tri((float)(1 << k) * in[2]);
+	} else {
+#pragma unroll
+		for (int k = 8; k < 12; ++k)
+			f[k - 8] = tri((float)(1 << k) * in[2]);
+		oneblob4(in[3], f + 4);
+		oneblob4(in[4], f + 8);
+		oneblob4(in[5], f + 12);
+		oneblob4(in[6], f + 16);
+		oneblob4(1.0f - expf(-in[7]), f + 20);
+#pragma unroll
+		for (int i = 0; i < 6; ++i)
+			f[24 + i] = in[8 + i];
+		f[30] = 1.0f, f[31] = 1.0f;
+	}
+#pragma unroll
+	for (int i = 0; i < 16; ++i)
+		o[i] = sm100::cvt_pack_f16x2(f[2 * i], f[2 * i + 1]);
+}
+
+// one-blob-32 of a single coordinate (32 features): gradient.comp:33-39 incl. the mismatched inverse radii 32 / 4
+__device__ __forceinline__ void encode_oneblob32_half(float x, uint32_t o[16]) {
+#pragma unroll
+	for (int i = 0; i < 16; ++i) {
+		const float l0 = (float)(2 * i) / 32.0f, r0 = (float)(2 * i + 1) / 32.0f, r1 = (float)(2 * i + 2) / 32.0f;
+		const float e0 = __fsub_rn(quartic_cdf(__fsub_rn(r0, x), 32.0f), quartic_cdf(__fsub_rn(l0, x), 4.0f));
+		const float e1 = __fsub_rn(quartic_cdf(__fsub_rn(r1, x), 32.0f), quartic_cdf(__fsub_rn(r0, x), 4.0f));
+		o[i] = sm100::cvt_pack_f16x2(e0, e1);
+	}
+}
+
 // one-blob-32 of u then v; note the mismatched inverse radii 32 / 4 are the reference's (gradient.comp:33-39).
 __device__ __forceinline__ void encode_oneblob32(float u, float v, uint32_t o[32]) {
 #pragma unroll

@@ -44,7 +44,7 @@ struct InferParams {
 
 struct GradParams {
 	uint64_t n;              // records in this batch (upper bound when d_count != nullptr)
-	const uint32_t *d_count; // optional device-resident count (clamped to n)
+	uint32_t *d_count;       // optional device-resident count (read clamped to n; written back clamped to batch_cap)
 	int in_mode, loss_kind;
 	float loss_scale;
 	const void *in;          // ENCODED: unused (TMA); UNPACKED: 14 floats per record at in_stride_bytes
@@ -70,16 +70,19 @@ struct AdamParams {
 	int use_ema;
 };
 
-struct ReduceParams {
-	const float *partials;
-	uint32_t num_partials;
-	float *gradients;      // [NRC_GRAD_STRIDE]
+// One launch of nrc_train_kernel = up to NRC_TRAIN_BATCH_COUNT dependent training batches (a frame):
+// per batch: gradient pass (per-CTA partial dW) -> grid barrier -> deterministic reduction of the partials
+// (+ optionally the optimizer step on the reduced gradient) -> grid barrier -> next batch with the new weights.
+struct TrainParams {
+	GradParams batch[NRC_TRAIN_BATCH_COUNT];
+	uint32_t num_batches;
+	int adam_mode[NRC_TRAIN_BATCH_COUNT]; // 0: reduce only, 1: + Adam/EMA step, 2: + also write use_weights
+	float *gradients;      // [NRC_GRAD_STRIDE] reduced dW (+ loss, count slots) of the LAST reduced batch
 	int accumulate;        // 1: gradients += sum (test/train_NV.comp semantics), 0: gradients = sum
 	uint32_t limit;        // number of leading elements to produce (20672 for a caller's dW, NRC_GRAD_STRIDE otherwise)
-	uint32_t *d_count;     // optional: clamped in place to batch_cap (nrc_train_prepare.comp:17-19)
-	uint32_t batch_cap;
-	int fuse_adam;         // 1: also run the optimizer step on the reduced gradient (single-GPU path, saves a launch)
-	AdamParams adam;
+	uint32_t batch_cap;    // d_count is clamped in place to this (nrc_train_prepare.comp:17-19)
+	AdamParams adam;       // use_weights / use_ema are taken from here when adam_mode == 2
+	uint32_t *grid_bar;    // {arrival count, generation}: zero-initialised, owned by the state object
 };
 
 struct SgdParams { // mlp_learning_an_image/optimize.comp:21-29
@@ -90,10 +93,8 @@ struct SgdParams { // mlp_learning_an_image/optimize.comp:21-29
 };
 
 cudaError_t launch_infer(const InferParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream);
-// returns the number of CTAs (= partial rows) through *num_partials
-cudaError_t launch_gradient(const GradParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, uint32_t *num_partials,
-                            cudaStream_t stream);
-cudaError_t launch_reduce(const ReduceParams &p, cudaStream_t stream);
+// cooperative launch: grid = min(#tiles of the largest batch, #SMs) CTAs, all co-resident
+cudaError_t launch_train(const TrainParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream);
 cudaError_t launch_adam(const AdamParams &p, cudaStream_t stream);
 cudaError_t launch_sgd(const SgdParams &p, cudaStream_t stream);
 uint32_t gradient_max_partials(int sms);

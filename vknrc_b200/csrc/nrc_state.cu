@@ -118,7 +118,7 @@ NrcState::NrcState(int device, Extent2D extent, uint64_t seed) : m_device(device
 	    !alloc((void **)&m_optimizer_entries, sizeof(NrcOptimizerEntry) * NRC_WEIGHT_COUNT) ||
 	    !alloc((void **)&m_gradients, sizeof(float) * NRC_GRAD_STRIDE) ||
 	    !alloc((void **)&m_partials, sizeof(float) * NRC_GRAD_STRIDE * gradient_max_partials(m_sms)) ||
-	    !alloc((void **)&m_done_counter, sizeof(uint32_t)))
+	    !alloc((void **)&m_sync_words, 4 * sizeof(uint32_t)))
 		return;
 	m_ok = true;
 	if (ResetMLPBuffers(seed) != NRC_OK)
@@ -127,7 +127,7 @@ NrcState::NrcState(int device, Extent2D extent, uint64_t seed) : m_device(device
 
 NrcState::~NrcState() {
 	cudaFree(m_weights), cudaFree(m_use_weights), cudaFree(m_optimizer_state), cudaFree(m_optimizer_entries);
-	cudaFree(m_gradients), cudaFree(m_partials), cudaFree(m_done_counter);
+	cudaFree(m_gradients), cudaFree(m_partials), cudaFree(m_sync_words);
 }
 
 // src/VkNRCState.cpp:39-44 (He-normal, sigma = sqrt(2 / 64)) and :46-58 (fp32 master = ema = init, fp16 copy RNE)
@@ -158,7 +158,7 @@ int NrcState::upload_initial(const float *w) {
 	NRC_CUDA_TRY(cudaMemcpy(m_use_weights, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice), sink);
 	NRC_CUDA_TRY(cudaMemcpy(m_optimizer_entries, e.data(), e.size() * sizeof(NrcOptimizerEntry), cudaMemcpyHostToDevice), sink);
 	NRC_CUDA_TRY(cudaMemcpy(m_optimizer_state, &st, sizeof(st), cudaMemcpyHostToDevice), sink);
-	NRC_CUDA_TRY(cudaMemset(m_done_counter, 0, sizeof(uint32_t)), sink);
+	NRC_CUDA_TRY(cudaMemset(m_sync_words, 0, 4 * sizeof(uint32_t)), sink);
 	return NRC_OK;
 }
 
@@ -195,39 +195,35 @@ int NrcState::Infer(InferParams p, const void *encoded_inputs, const __half *wei
 	return NRC_OK;
 }
 
-int NrcState::Gradient(GradParams p, const void *encoded_inputs, const __half *weights, float *gradients, bool accumulate, uint32_t *d_count,
-                       uint32_t batch_cap, cudaStream_t stream, int fused_step) {
+int NrcState::Train(TrainParams tp, const void *encoded_inputs, const __half *weights, cudaStream_t stream) {
 	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
+	if (tp.num_batches == 0 || tp.num_batches > NRC_TRAIN_BATCH_COUNT)
+		return fail(NRC_ERR_INVALID_ARGUMENT, "Train: num_batches must be 1..4");
+	const bool encoded = tp.batch[0].in_mode == NRC_IN_ENCODED;
+	if (encoded && tp.num_batches != 1)
+		return fail(NRC_ERR_INVALID_ARGUMENT, "Train: pre-encoded inputs are single-batch");
 	CUtensorMap tm_w, tm_in;
 	std::string err;
 	int rc = make_weight_tensor_map(&tm_w, weights, &err);
 	if (rc == NRC_OK)
-		rc = p.in_mode == NRC_IN_ENCODED ? make_input_tensor_map(&tm_in, encoded_inputs, p.n, &err) : (tm_in = tm_w, NRC_OK);
+		rc = encoded ? make_input_tensor_map(&tm_in, encoded_inputs, tp.batch[0].n, &err) : (tm_in = tm_w, NRC_OK);
 	if (rc != NRC_OK)
 		return fail(rc, err);
 	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
-	p.partials = m_partials;
-	p.d_count = d_count;
-	uint32_t num_partials = 0;
-	NRC_CUDA_TRY(launch_gradient(p, tm_w, tm_in, m_sms, &num_partials, stream), sink);
-	ReduceParams r{};
-	r.partials = m_partials, r.num_partials = num_partials, r.gradients = gradients, r.accumulate = accumulate ? 1 : 0;
-	r.limit = accumulate ? NRC_WEIGHT_COUNT : NRC_GRAD_STRIDE;
-	r.d_count = d_count, r.batch_cap = batch_cap;
-	if (fused_step) {
-		r.fuse_adam = 1;
-		r.adam.gradients = gradients, r.adam.entries = m_optimizer_entries, r.adam.opt_state = m_optimizer_state;
-		r.adam.done_counter = m_done_counter, r.adam.weights = m_weights;
-		r.adam.use_weights = fused_step == 2 ? m_use_weights : nullptr, r.adam.use_ema = m_use_ema_weights ? 1 : 0;
-	}
-	NRC_CUDA_TRY(launch_reduce(r, stream), sink);
+	for (uint32_t b = 0; b < tp.num_batches; ++b)
+		tp.batch[b].partials = m_partials;
+	tp.grid_bar = m_sync_words + 2;
+	tp.adam.gradients = tp.gradients, tp.adam.entries = m_optimizer_entries, tp.adam.opt_state = m_optimizer_state;
+	tp.adam.done_counter = m_sync_words, tp.adam.weights = m_weights, tp.adam.use_weights = m_use_weights;
+	tp.adam.use_ema = m_use_ema_weights ? 1 : 0;
+	NRC_CUDA_TRY(launch_train(tp, tm_w, tm_in, m_sms, stream), sink);
 	return NRC_OK;
 }
 
 int NrcState::AdamStep(bool write_use_weights, cudaStream_t stream) {
 	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
 	AdamParams a{};
-	a.gradients = m_gradients, a.entries = m_optimizer_entries, a.opt_state = m_optimizer_state, a.done_counter = m_done_counter;
+	a.gradients = m_gradients, a.entries = m_optimizer_entries, a.opt_state = m_optimizer_state, a.done_counter = m_sync_words;
 	a.weights = m_weights, a.use_weights = write_use_weights ? m_use_weights : nullptr, a.use_ema = m_use_ema_weights ? 1 : 0;
 	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
 	NRC_CUDA_TRY(launch_adam(a, stream), sink);
@@ -366,10 +362,12 @@ int nrc_mlp_gradient_encoded(const void *d_weights, float *d_dw, const void *d_i
 	NrcState *s = scratch_state(&rc);
 	if (!s)
 		return rc;
-	GradParams p{};
+	TrainParams tp{};
+	GradParams &p = tp.batch[0];
 	p.n = n, p.in_mode = NRC_IN_ENCODED, p.loss_kind = NRC_LOSS_L2, p.loss_scale = 1.0f;
 	p.target = d_targets, p.target_stride_bytes = 6, p.target_is_f16 = 1;
-	return s->Gradient(p, d_inputs, (const __half *)d_weights, d_dw, /*accumulate=*/true, nullptr, 0, (cudaStream_t)stream);
+	tp.num_batches = 1, tp.gradients = d_dw, tp.accumulate = 1, tp.limit = NRC_WEIGHT_COUNT; // dw += (test/train_NV.comp)
+	return s->Train(tp, d_inputs, (const __half *)d_weights, (cudaStream_t)stream);
 }
 
 int nrc_infer_encoded(nrc_handle_t h, const void *d_inputs, void *d_out, uint64_t n, int clamp_output, void *stream) {
@@ -414,34 +412,51 @@ int nrc_infer_scatter_unpacked(nrc_handle_t h, const uint32_t *d_dst, uint32_t d
 	return h->state.Infer(p, nullptr, h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
 }
 
-static int gradient_unpacked_impl(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets, uint32_t target_stride,
-                                  uint32_t *d_count, uint32_t max_count, void *stream, int fused_step) {
-	NRC_REQUIRE(h, "null handle");
-	NRC_REQUIRE(max_count == 0 || (d_inputs && d_targets), "nrc_gradient_unpacked: null buffer");
-	NRC_REQUIRE(input_stride >= 56 && input_stride % 8 == 0 && ((uintptr_t)d_inputs & 7u) == 0, "nrc_gradient_unpacked: inputs must be 8-byte aligned, stride >= 56 and a multiple of 8");
-	NRC_REQUIRE(target_stride >= 12 && target_stride % 4 == 0, "nrc_gradient_unpacked: target stride must be >= 12 and a multiple of 4");
-	GradParams p{};
-	p.n = max_count, p.in_mode = NRC_IN_UNPACKED, p.loss_kind = NRC_LOSS_RELATIVE_L2_LUMINANCE, p.loss_scale = NRC_LOSS_SCALE;
+static int check_unpacked_args(const char *who, const void *d_inputs, uint32_t input_stride, const void *d_targets, uint32_t target_stride,
+                               uint32_t max_count) {
+	(void)who;
+	NRC_REQUIRE(max_count == 0 || (d_inputs && d_targets), "training: null record / target buffer");
+	NRC_REQUIRE(input_stride >= 56 && input_stride % 8 == 0 && ((uintptr_t)d_inputs & 7u) == 0,
+	            "training: inputs must be 8-byte aligned, stride >= 56 and a multiple of 8");
+	NRC_REQUIRE(target_stride >= 12 && target_stride % 4 == 0 && ((uintptr_t)d_targets & 3u) == 0,
+	            "training: targets must be 4-byte aligned, stride >= 12 and a multiple of 4");
+	return NRC_OK;
+}
+static void fill_unpacked_batch(nrc_handle_t h, GradParams &p, const void *d_inputs, uint32_t input_stride, const void *d_targets,
+                                uint32_t target_stride, uint32_t *d_count, uint32_t max_count) {
+	p.n = max_count, p.d_count = d_count, p.in_mode = NRC_IN_UNPACKED, p.loss_kind = NRC_LOSS_RELATIVE_L2_LUMINANCE, p.loss_scale = NRC_LOSS_SCALE;
 	p.in = d_inputs, p.in_stride_bytes = input_stride, p.target = d_targets, p.target_stride_bytes = target_stride, p.target_is_f16 = 0;
 	p.y_out = h->state.GetPredictionCapture();
-	return h->state.Gradient(p, nullptr, h->state.GetWeightBuffer(), h->state.GetGradientBuffer(), false, d_count, max_count, (cudaStream_t)stream,
-	                         fused_step);
+}
+// adam_mode: 0 = gradient + reduction only, 1 = + Adam/EMA step, 2 = + use_weights
+static int train_unpacked_impl(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets, uint32_t target_stride,
+                               uint32_t *d_count, uint32_t max_count, void *stream, int adam_mode) {
+	NRC_REQUIRE(h, "null handle");
+	int rc = check_unpacked_args("train", d_inputs, input_stride, d_targets, target_stride, max_count);
+	if (rc != NRC_OK)
+		return rc;
+	TrainParams tp{};
+	fill_unpacked_batch(h, tp.batch[0], d_inputs, input_stride, d_targets, target_stride, d_count, max_count);
+	tp.num_batches = 1, tp.adam_mode[0] = adam_mode, tp.gradients = h->state.GetGradientBuffer(), tp.limit = NRC_GRAD_STRIDE, tp.batch_cap = max_count;
+	return h->state.Train(tp, nullptr, h->state.GetWeightBuffer(), (cudaStream_t)stream);
 }
 
 int nrc_gradient_unpacked(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets, uint32_t target_stride,
                           uint32_t *d_count, uint32_t max_count, void *stream) {
-	return gradient_unpacked_impl(h, d_inputs, input_stride, d_targets, target_stride, d_count, max_count, stream, 0);
+	return train_unpacked_impl(h, d_inputs, input_stride, d_targets, target_stride, d_count, max_count, stream, 0);
 }
 
 int nrc_gradient_encoded(nrc_handle_t h, const void *d_inputs, const void *d_targets, uint32_t *d_count, uint32_t max_count, int relative_loss,
                          void *stream) {
 	NRC_REQUIRE(h, "null handle");
 	NRC_REQUIRE(max_count == 0 || (d_inputs && d_targets), "nrc_gradient_encoded: null buffer");
-	GradParams p{};
-	p.n = max_count, p.in_mode = NRC_IN_ENCODED, p.loss_kind = relative_loss ? NRC_LOSS_RELATIVE_L2_LUMINANCE : NRC_LOSS_L2;
+	TrainParams tp{};
+	GradParams &p = tp.batch[0];
+	p.n = max_count, p.d_count = d_count, p.in_mode = NRC_IN_ENCODED, p.loss_kind = relative_loss ? NRC_LOSS_RELATIVE_L2_LUMINANCE : NRC_LOSS_L2;
 	p.loss_scale = NRC_LOSS_SCALE, p.target = d_targets, p.target_stride_bytes = 6, p.target_is_f16 = 1;
 	p.y_out = h->state.GetPredictionCapture();
-	return h->state.Gradient(p, d_inputs, h->state.GetWeightBuffer(), h->state.GetGradientBuffer(), false, d_count, max_count, (cudaStream_t)stream);
+	tp.num_batches = 1, tp.gradients = h->state.GetGradientBuffer(), tp.limit = NRC_GRAD_STRIDE, tp.batch_cap = max_count;
+	return h->state.Train(tp, d_inputs, h->state.GetWeightBuffer(), (cudaStream_t)stream);
 }
 
 int nrc_adam_step(nrc_handle_t h, int write_use_weights, void *stream) {
@@ -449,21 +464,43 @@ int nrc_adam_step(nrc_handle_t h, int write_use_weights, void *stream) {
 	return h->state.AdamStep(write_use_weights != 0, (cudaStream_t)stream);
 }
 
-// gradient kernel + ONE kernel that reduces the partials deterministically and applies Adam/EMA (2 launches per batch)
+// ONE launch: gradient pass, grid barrier, deterministic reduction of the partials and the Adam/EMA step
 int nrc_train_batch_unpacked(nrc_handle_t h, const void *d_inputs, uint32_t input_stride, const void *d_targets, uint32_t target_stride,
                              uint32_t *d_count, uint32_t max_count, int write_use_weights, void *stream) {
-	return gradient_unpacked_impl(h, d_inputs, input_stride, d_targets, target_stride, d_count, max_count, stream, write_use_weights ? 2 : 1);
+	return train_unpacked_impl(h, d_inputs, input_stride, d_targets, target_stride, d_count, max_count, stream, write_use_weights ? 2 : 1);
+}
+
+// ONE launch for the whole frame: the four dependent batches of src/rg/NRCRenderGraph.cpp:57-70, use_weights published
+// by the last one only (:66-68)
+int nrc_train_frame_unpacked(nrc_handle_t h, const void *const d_inputs[4], uint32_t input_stride, const void *const d_targets[4],
+                             uint32_t target_stride, uint32_t *const d_counts[4], uint32_t max_count, void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	NRC_REQUIRE(d_inputs && d_targets, "nrc_train_frame_unpacked: null buffer table");
+	TrainParams tp{};
+	for (int b = 0; b < NRC_TRAIN_BATCH_COUNT; ++b) {
+		int rc = check_unpacked_args("frame", d_inputs[b], input_stride, d_targets[b], target_stride, max_count);
+		if (rc != NRC_OK)
+			return rc;
+		fill_unpacked_batch(h, tp.batch[b], d_inputs[b], input_stride, d_targets[b], target_stride, d_counts ? d_counts[b] : nullptr, max_count);
+		if (tp.batch[b].y_out) // the capture buffer holds one batch: keep the last batch's predictions
+			tp.batch[b].y_out = b == NRC_TRAIN_BATCH_COUNT - 1 ? tp.batch[b].y_out : nullptr;
+		tp.adam_mode[b] = b == NRC_TRAIN_BATCH_COUNT - 1 ? 2 : 1;
+	}
+	tp.num_batches = NRC_TRAIN_BATCH_COUNT, tp.gradients = h->state.GetGradientBuffer(), tp.limit = NRC_GRAD_STRIDE, tp.batch_cap = max_count;
+	return h->state.Train(tp, nullptr, h->state.GetWeightBuffer(), (cudaStream_t)stream);
 }
 
 int nrc_image_train_step(nrc_handle_t h, const void *d_image_rgba8, uint32_t image_w, uint32_t image_h, uint32_t seed_x, uint32_t seed_y,
                          uint32_t batch, float lr, void *stream) {
 	NRC_REQUIRE(h, "null handle");
 	NRC_REQUIRE(d_image_rgba8 && image_w && image_h && batch, "nrc_image_train_step: bad image or batch");
-	GradParams p{};
+	TrainParams tp{};
+	GradParams &p = tp.batch[0];
 	p.n = batch, p.in_mode = NRC_IN_IMAGE_RANDOM, p.loss_kind = NRC_LOSS_L2, p.loss_scale = 1.0f;
 	p.seed_x = seed_x, p.seed_y = seed_y, p.image_rgba8 = (const uint8_t *)d_image_rgba8, p.image_w = image_w, p.image_h = image_h;
 	p.y_out = h->state.GetPredictionCapture();
-	int rc = h->state.Gradient(p, nullptr, h->state.GetWeightBuffer(), h->state.GetGradientBuffer(), false, nullptr, 0, (cudaStream_t)stream);
+	tp.num_batches = 1, tp.gradients = h->state.GetGradientBuffer(), tp.limit = NRC_GRAD_STRIDE;
+	int rc = h->state.Train(tp, nullptr, h->state.GetWeightBuffer(), (cudaStream_t)stream);
 	if (rc != NRC_OK)
 		return rc;
 	return h->state.SgdStep(lr, (float)batch, (cudaStream_t)stream);

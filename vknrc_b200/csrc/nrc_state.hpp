@@ -66,10 +66,10 @@ public:
 
 	// ---- hot path
 	int Infer(InferParams p, const void *encoded_inputs, const __half *weights, cudaStream_t stream);
-	// fused_step: 0 = gradient + reduction only; 1 / 2 = also the Adam step inside the reduction kernel
-	// (2 = write use_weights as well)
-	int Gradient(GradParams p, const void *encoded_inputs, const __half *weights, float *gradients, bool accumulate, uint32_t *d_count,
-	             uint32_t batch_cap, cudaStream_t stream, int fused_step = 0);
+	// One cooperative launch of nrc_train_kernel: tp.batch[0..num_batches) (inputs / targets / counts / loss), tp.adam_mode,
+	// tp.accumulate / limit / batch_cap and tp.gradients are the caller's; partials, barrier words and the optimizer
+	// buffers are filled in here. `weights` is the fp16 buffer the forward / backward passes read.
+	int Train(TrainParams tp, const void *encoded_inputs, const __half *weights, cudaStream_t stream);
 	int AdamStep(bool write_use_weights, cudaStream_t stream);
 	int SgdStep(float lr, float batch, cudaStream_t stream);
 	void SetPredictionCapture(float *d) { m_prediction_capture = d; }
@@ -92,7 +92,7 @@ private:
 	NrcOptimizerState *m_optimizer_state{nullptr};
 	NrcOptimizerEntry *m_optimizer_entries{nullptr};
 	float *m_gradients{nullptr}, *m_partials{nullptr};
-	uint32_t *m_done_counter{nullptr};
+	uint32_t *m_sync_words{nullptr}; // [0] optimizer "last CTA" counter, [2..3] grid barrier {count, generation}
 	float *m_prediction_capture{nullptr};
 
 	uint32_t m_seed{0};
