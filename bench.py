@@ -10,7 +10,8 @@ Workload (config.workload): BASELINE.json configs[2] -- 1920x1080 = 2 073 600 sy
 max over ranks); `e2e` = the same call fed from pinned HOST buffers with the H2D / D2H copies inside the timed region.
 `extra` carries the other half of the metric (training records/s on configs[3], 4 x 16384 records per frame) and the
 fused-encode inference path. Multi-GPU: queries (and training records) are sharded by index range, one process per
-GPU, weak scaling; training all-reduces the 82 944-byte gradient buffer over NCCL before a replicated Adam step.
+GPU, weak scaling; training all-reduces the 82 944-byte gradient buffer INSIDE the training kernel (peer-mapped inboxes
+over NVLink) before a replicated Adam step; the NCCL version of the same frame is timed beside it.
 
 --impl reference times the reference's OWN CPU implementation of the same path (test/main.cpp `Evaluate`, compiled
 unmodified into oracle/_ref) on the host cores, on a bounded sample of the same workload.
@@ -224,14 +225,14 @@ def main():
             nb = nrc.TRAIN_BATCH_SIZE
             trec = torch.rand((4, nb, 14), device=dev, generator=g)
             ttgt = torch.rand((4, nb, 3), device=dev, generator=g)
-            gt = st.gradient_tensor()
+
+            trecs, ttgts = [trec[b] for b in range(4)], [ttgt[b] for b in range(4)]
+            if world > 1:
+                st.comm_connect()  # peer-mapped inboxes: the gradient all-reduce runs inside the training kernel
 
             def train_frame():
-                for b in range(4):
-                    st.gradient_unpacked(trec[b], ttgt[b])
-                    if world > 1:
-                        dist.all_reduce(gt)  # 20 736 fp32: dW + loss + record count
-                    st.adam_step(write_use_weights=(b == 3))
+                # the whole frame (4 x [gradient -> reduce -> (NVLink all-reduce) -> Adam]) is ONE cooperative kernel launch
+                st.train_frame_unpacked(trecs, ttgts)
             ms_t = timed(train_frame, max(10, K // 4), 3)
             extra["train_records_per_s"] = world * 4 * nb / (ms_t * 1e-3)
             extra["train_ms_per_frame_4x16384"] = ms_t
@@ -242,11 +243,18 @@ def main():
             btgt = torch.rand((big, 3), device=dev, generator=g)
 
             def train_big():
-                st.gradient_unpacked(brec, btgt)
-                if world > 1:
-                    dist.all_reduce(gt)
-                st.adam_step(True)
+                st.train_batch_unpacked(brec, btgt, write_use_weights=True)
             ms_b = timed(train_big, 5, 2)
+            if world > 1:  # the stock-collective version of the same frame, for comparison: gradient -> NCCL all-reduce -> Adam
+                st_split = nrc.NrcState(local, (1920, 1080), seed=1234)
+                gt = st_split.gradient_tensor()
+
+                def train_frame_nccl():
+                    for b in range(4):
+                        st_split.gradient_unpacked(trec[b], ttgt[b])
+                        dist.all_reduce(gt)  # 20 736 fp32: dW + loss + record count
+                        st_split.adam_step(write_use_weights=(b == 3))
+                extra["train_ms_per_frame_nccl_split"] = timed(train_frame_nccl, max(10, K // 4), 3)
             extra["train_2p20_records_per_s"] = world * big / (ms_b * 1e-3)
             extra["train_2p20_tflops_per_gpu"] = big * FLOP_PER_TRAIN_RECORD / (ms_b * 1e-3) / 1e12
 

@@ -122,6 +122,20 @@ int nrc_train_frame_unpacked(nrc_handle_t h, const void *const d_inputs[4], uint
 /* optional fp32 [max_count][3] buffer that receives the (unclamped) training predictions of the next gradient call */
 void nrc_set_prediction_capture(nrc_handle_t h, float *d_predictions);
 
+/* ---- multi-GPU (one process per GPU; records of every batch sharded per GPU) ----
+ * The reference is single-GPU; this is the exchange step of the data-parallel path. nrc_comm_init allocates this rank's
+ * inbox and returns its 64-byte CUDA IPC handle; the caller gathers the handles of all ranks (rank order) through its
+ * own channel and passes them to nrc_comm_connect on every rank (then synchronises the ranks once). From then on every
+ * nrc_gradient_* / nrc_train_* call all-reduces the reduced gradient (dW, loss sum, record count) with the peers INSIDE
+ * the training kernel - peer-mapped stores over NVLink, per-block flags, fixed rank-order sum, so the result is
+ * bit-identical on all ranks - and the optimizer step that follows is replicated. All ranks must make the same sequence
+ * of training calls with the same max_count. */
+uint32_t nrc_comm_handle_bytes(void);
+int nrc_comm_init(nrc_handle_t h, uint32_t rank, uint32_t world, void *out_handle);
+int nrc_comm_connect(nrc_handle_t h, const void *all_handles);
+int nrc_comm_shutdown(nrc_handle_t h);
+uint32_t nrc_comm_world(nrc_handle_t h);
+
 /* ---- learn-an-image harness (test/mlp_learning_an_image/{gradient,optimize,inference}.comp) ----
  * one training step: `batch` random uv samples (pcg2d stream of push-constant seeds), one-blob-32 encoding,
  * bilinear RGBA8 target, L2 loss, SGD lr on the fp32 master weights; inference over a width x width grid to RGBA8. */

@@ -284,7 +284,7 @@ def test_gradient_unpacked_and_adam_match_oracle(nrc, oracle_mod, state):
 
 
 def test_fused_train_batch_equals_split_path(nrc, state):
-    """nrc_train_batch_unpacked (gradient + ONE reduce-and-Adam kernel) must equal nrc_gradient_unpacked followed by
+    """nrc_train_batch_unpacked (gradient, reduction and Adam in ONE launch) must equal nrc_gradient_unpacked followed by
     nrc_adam_step (the multi-GPU path, with the all-reduce in between) bit for bit."""
     w32 = he_weights(63)
     rec, tgt = dev(random_records(14, 5000)), torch.rand((5000, 3), device="cuda")
@@ -305,6 +305,38 @@ def test_fused_train_batch_equals_split_path(nrc, state):
     assert np.array_equal(a["use_weights"].view(np.uint16), b["use_weights"].view(np.uint16))
     assert a["optimizer_state"] == b["optimizer_state"] and a["optimizer_state"]["t"] == 3
     assert np.array_equal(a["gradients"], b["gradients"])
+
+
+def test_train_frame_equals_four_batches(nrc, state):
+    """nrc_train_frame_unpacked (the frame's four dependent batches in ONE launch, NRCRenderGraph.cpp:57-70) must equal
+    four nrc_train_batch_unpacked calls bit for bit - including an empty batch in the middle (skipped entirely,
+    nrc_optimize.comp:33-34), an over-full one (clamped, nrc_train_prepare.comp:17-19) and use_weights written by the
+    last batch only."""
+    w32 = he_weights(67)
+    nb = nrc.TRAIN_BATCH_SIZE
+    recs = [dev(random_records(20 + b, nb)) for b in range(4)]
+    tgts = [torch.rand((nb, 3), device="cuda", generator=torch.Generator(device="cuda").manual_seed(b)) for b in range(4)]
+    counts_host = [nb, 0, 100000, 777]
+    results = []
+    for frame in (True, False):
+        state.set_weights(w32)
+        state.set_use_ema_weights(True)
+        counts = [torch.tensor([c], dtype=torch.int32, device="cuda") for c in counts_host]
+        for _ in range(2):  # two frames
+            if frame:
+                state.train_frame_unpacked(recs, tgts, counts)
+            else:
+                for b in range(4):
+                    state.train_batch_unpacked(recs[b], tgts[b], count=counts[b], write_use_weights=(b == 3))
+        results.append((state.download(), [int(c.item()) for c in counts]))
+    (a, ca), (b, cb) = results
+    assert ca == cb == [nb, 0, nb, 777]
+    assert np.array_equal(a["optimizer_entries"].view(np.uint32), b["optimizer_entries"].view(np.uint32))
+    assert np.array_equal(a["weights"].view(np.uint16), b["weights"].view(np.uint16))
+    assert np.array_equal(a["use_weights"].view(np.uint16), b["use_weights"].view(np.uint16))
+    assert a["optimizer_state"] == b["optimizer_state"] and a["optimizer_state"]["t"] == 6
+    assert np.array_equal(a["gradients"], b["gradients"]) and a["gradients"][nrc.GRAD_COUNT_SLOT] == 777
+    assert not np.array_equal(a["weights"].view(np.uint16), a["use_weights"].view(np.uint16))  # EMA weights were published
 
 
 def test_empty_and_overfull_batches(nrc, oracle_mod, state):

@@ -80,6 +80,11 @@ SIGNATURES = {
                                            C.c_int, C.c_void_p]),
     "nrc_train_frame_unpacked": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32,
                                            C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p]),
+    "nrc_comm_handle_bytes": (C.c_uint32, []),
+    "nrc_comm_init": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
+    "nrc_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nrc_comm_shutdown": (C.c_int, [C.c_void_p]),
+    "nrc_comm_world": (C.c_uint32, [C.c_void_p]),
     "nrc_set_prediction_capture": (None, [C.c_void_p, C.c_void_p]),
     "nrc_image_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.c_float, C.c_void_p]),
@@ -279,6 +284,25 @@ class NrcState:
         tgs = (C.c_void_p * 4)(*[_ptr(t) for t in targets])
         cns = (C.c_void_p * 4)(*[_ptr(t) for t in counts]) if counts is not None else None
         _check(lib().nrc_train_frame_unpacked(self._h, ins, input_stride, tgs, target_stride, cns, n, _stream()))
+
+    # ---- multi-GPU (one process per GPU)
+    def comm_connect(self, group=None):
+        """Sets up the in-kernel NVLink all-reduce between the ranks of a torch.distributed group: every rank allocates
+        its inbox, the 64-byte IPC handles are all-gathered (plumbing), every rank maps its peers' inboxes."""
+        import torch.distributed as dist
+        from .dist import exchange_handles
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        buf = C.create_string_buffer(lib().nrc_comm_handle_bytes())
+        _check(lib().nrc_comm_init(self._h, rank, world, buf))
+        handles = exchange_handles(buf.raw, group)
+        _check(lib().nrc_comm_connect(self._h, b"".join(handles)))
+        dist.barrier(group)  # nobody pushes before everybody has mapped
+
+    def comm_shutdown(self):
+        _check(lib().nrc_comm_shutdown(self._h))
+
+    def comm_world(self) -> int:
+        return lib().nrc_comm_world(self._h)
 
     # ---- learn-an-image
     def image_train_step(self, image_rgba8, seed_x: int, seed_y: int, batch: int = 16384, lr: float = 0.01):

@@ -70,6 +70,24 @@ struct AdamParams {
 	int use_ema;
 };
 
+// Multi-GPU exchange (one process per GPU, records of every batch sharded per GPU): after the local reduction each
+// rank pushes its reduced 64-float blocks straight into every peer's inbox over NVLink (peer-mapped device memory)
+// as 8-byte {value, epoch} words - one NVLink traversal, no fence, the receiver spins on the very word it needs -
+// and adds the R copies in rank order: an all-reduce fused into the training kernel, bit-identical on every rank,
+// followed by a replicated Adam step. A per-block word carries the rank's record count the same way.
+// Comm buffer of a rank (identical layout everywhere, zero-initialised; parity = epoch & 1 double-buffers it):
+//   uint64_t data [2 parities][NRC_MAX_RANKS sources][NRC_GRAD_STRIDE]        (epoch << 32 | float bits)
+//   uint64_t count[2 parities][NRC_MAX_RANKS sources][NRC_GRAD_STRIDE / 64]   (epoch << 32 | count float bits)
+#define NRC_MAX_RANKS 8
+struct CommParams {
+	uint32_t rank, world;           // world <= 1: no exchange
+	uint32_t epoch_base;            // batch b of this launch uses epoch epoch_base + b (never 0)
+	uint64_t *inbox[NRC_MAX_RANKS]; // comm buffer of every rank as mapped into this process (inbox[rank] = the local one)
+};
+constexpr size_t kCommDataWords = 2ull * NRC_MAX_RANKS * NRC_GRAD_STRIDE;
+constexpr size_t kCommCountWords = 2ull * NRC_MAX_RANKS * (NRC_GRAD_STRIDE / 64);
+constexpr size_t kCommBytes = (kCommDataWords + kCommCountWords) * sizeof(uint64_t);
+
 // One launch of nrc_train_kernel = up to NRC_TRAIN_BATCH_COUNT dependent training batches (a frame):
 // per batch: gradient pass (per-CTA partial dW) -> grid barrier -> deterministic reduction of the partials
 // (+ optionally the optimizer step on the reduced gradient) -> grid barrier -> next batch with the new weights.
@@ -83,6 +101,7 @@ struct TrainParams {
 	uint32_t batch_cap;    // d_count is clamped in place to this (nrc_train_prepare.comp:17-19)
 	AdamParams adam;       // use_weights / use_ema are taken from here when adam_mode == 2
 	uint32_t *grid_bar;    // {arrival count, generation}: zero-initialised, owned by the state object
+	CommParams comm;
 };
 
 struct SgdParams { // mlp_learning_an_image/optimize.comp:21-29

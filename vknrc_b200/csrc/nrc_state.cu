@@ -128,6 +128,49 @@ NrcState::NrcState(int device, Extent2D extent, uint64_t seed) : m_device(device
 NrcState::~NrcState() {
 	cudaFree(m_weights), cudaFree(m_use_weights), cudaFree(m_optimizer_state), cudaFree(m_optimizer_entries);
 	cudaFree(m_gradients), cudaFree(m_partials), cudaFree(m_sync_words);
+	CommShutdown();
+}
+
+int NrcState::CommInit(uint32_t rank, uint32_t world, cudaIpcMemHandle_t *out_handle) {
+	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
+	if (world < 1 || world > NRC_MAX_RANKS || rank >= world || !out_handle)
+		return fail(NRC_ERR_INVALID_ARGUMENT, "CommInit: need rank < world <= 8 and a handle to fill");
+	CommShutdown();
+	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
+	NRC_CUDA_TRY(cudaMalloc((void **)&m_comm_local, kCommBytes), sink);
+	NRC_CUDA_TRY(cudaMemset(m_comm_local, 0, kCommBytes), sink);
+	NRC_CUDA_TRY(cudaDeviceSynchronize(), sink);
+	NRC_CUDA_TRY(cudaIpcGetMemHandle(out_handle, m_comm_local), sink);
+	m_comm_rank = rank, m_comm_world = world, m_comm_epoch = 0;
+	return NRC_OK;
+}
+int NrcState::CommConnect(const cudaIpcMemHandle_t *all_handles) {
+	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
+	if (!m_comm_local || !all_handles)
+		return fail(NRC_ERR_INVALID_ARGUMENT, "CommConnect: call CommInit first");
+	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
+	for (uint32_t r = 0; r < m_comm_world; ++r) {
+		if (r == m_comm_rank) {
+			m_comm_inbox[r] = m_comm_local;
+			continue;
+		}
+		void *p = nullptr;
+		NRC_CUDA_TRY(cudaIpcOpenMemHandle(&p, all_handles[r], cudaIpcMemLazyEnablePeerAccess), sink);
+		m_comm_inbox[r] = (uint64_t *)p;
+	}
+	m_comm_connected = true;
+	return NRC_OK;
+}
+int NrcState::CommShutdown() {
+	for (uint32_t r = 0; r < NRC_MAX_RANKS; ++r) {
+		if (m_comm_inbox[r] && m_comm_inbox[r] != m_comm_local)
+			cudaIpcCloseMemHandle(m_comm_inbox[r]);
+		m_comm_inbox[r] = nullptr;
+	}
+	if (m_comm_local)
+		cudaFree(m_comm_local);
+	m_comm_local = nullptr, m_comm_connected = false, m_comm_world = 1, m_comm_rank = 0;
+	return NRC_OK;
 }
 
 // src/VkNRCState.cpp:39-44 (He-normal, sigma = sqrt(2 / 64)) and :46-58 (fp32 master = ema = init, fp16 copy RNE)
@@ -216,6 +259,13 @@ int NrcState::Train(TrainParams tp, const void *encoded_inputs, const __half *we
 	tp.adam.gradients = tp.gradients, tp.adam.entries = m_optimizer_entries, tp.adam.opt_state = m_optimizer_state;
 	tp.adam.done_counter = m_sync_words, tp.adam.weights = m_weights, tp.adam.use_weights = m_use_weights;
 	tp.adam.use_ema = m_use_ema_weights ? 1 : 0;
+	tp.comm = CommParams{};
+	if (m_comm_connected && m_comm_world > 1 && !tp.accumulate) { // (the handle-less test-harness calls never exchange)
+		tp.comm.rank = m_comm_rank, tp.comm.world = m_comm_world, tp.comm.epoch_base = m_comm_epoch + 1;
+		for (uint32_t r = 0; r < m_comm_world; ++r)
+			tp.comm.inbox[r] = m_comm_inbox[r];
+		m_comm_epoch += tp.num_batches;
+	}
 	NRC_CUDA_TRY(launch_train(tp, tm_w, tm_in, m_sms, stream), sink);
 	return NRC_OK;
 }
@@ -316,6 +366,23 @@ void nrc_set_prediction_capture(nrc_handle_t h, float *d) {
 	if (h)
 		h->state.SetPredictionCapture(d);
 }
+
+// ---- multi-GPU exchange set-up (one process per GPU; the 64-byte handles travel through the caller's own channel,
+// e.g. torch.distributed.all_gather, MPI or a socket)
+uint32_t nrc_comm_handle_bytes(void) { return (uint32_t)sizeof(cudaIpcMemHandle_t); }
+int nrc_comm_init(nrc_handle_t h, uint32_t rank, uint32_t world, void *out_handle) {
+	NRC_REQUIRE(h && out_handle, "nrc_comm_init: null argument");
+	return h->state.CommInit(rank, world, (cudaIpcMemHandle_t *)out_handle);
+}
+int nrc_comm_connect(nrc_handle_t h, const void *all_handles) {
+	NRC_REQUIRE(h && all_handles, "nrc_comm_connect: null argument");
+	return h->state.CommConnect((const cudaIpcMemHandle_t *)all_handles);
+}
+int nrc_comm_shutdown(nrc_handle_t h) {
+	NRC_REQUIRE(h, "null handle");
+	return h->state.CommShutdown();
+}
+uint32_t nrc_comm_world(nrc_handle_t h) { return h ? h->state.comm_world() : 0u; }
 
 // ---- handle-less test-harness kernels: a lazily created per-device scratch state supplies the partial buffers
 static NrcState *scratch_state(int *rc) {

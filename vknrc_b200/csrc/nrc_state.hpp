@@ -70,6 +70,12 @@ public:
 	// tp.accumulate / limit / batch_cap and tp.gradients are the caller's; partials, barrier words and the optimizer
 	// buffers are filled in here. `weights` is the fp16 buffer the forward / backward passes read.
 	int Train(TrainParams tp, const void *encoded_inputs, const __half *weights, cudaStream_t stream);
+	// ---- multi-GPU: one process per GPU; after CommConnect every Train launch all-reduces the reduced gradient with
+	// the peers inside the kernel (peer-mapped inboxes over NVLink) before the replicated optimizer step.
+	int CommInit(uint32_t rank, uint32_t world, cudaIpcMemHandle_t *out_handle); // allocates the local inbox
+	int CommConnect(const cudaIpcMemHandle_t *all_handles);                      // world handles in rank order
+	int CommShutdown();
+	uint32_t comm_world() const { return m_comm_connected ? m_comm_world : 1; }
 	int AdamStep(bool write_use_weights, cudaStream_t stream);
 	int SgdStep(float lr, float batch, cudaStream_t stream);
 	void SetPredictionCapture(float *d) { m_prediction_capture = d; }
@@ -94,6 +100,11 @@ private:
 	float *m_gradients{nullptr}, *m_partials{nullptr};
 	uint32_t *m_sync_words{nullptr}; // [0] optimizer "last CTA" counter, [2..3] grid barrier {count, generation}
 	float *m_prediction_capture{nullptr};
+
+	uint64_t *m_comm_local{nullptr};
+	uint64_t *m_comm_inbox[NRC_MAX_RANKS]{};
+	uint32_t m_comm_rank{0}, m_comm_world{1}, m_comm_epoch{0};
+	bool m_comm_connected{false};
 
 	uint32_t m_seed{0};
 	std::mt19937 m_rng;

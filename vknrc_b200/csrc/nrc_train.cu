@@ -146,6 +146,20 @@ __device__ __forceinline__ float ld_cg(const float *p) { // L2 only: the partial
 	return v;
 }
 
+// 8-byte {epoch, payload} words exchanged with peer GPUs: a single store is atomic, so the receiver can spin on the word
+__device__ __forceinline__ void st_peer(uint64_t *p, uint64_t v) { asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+__device__ __forceinline__ uint32_t wait_peer(const uint64_t *p, uint32_t epoch) {
+	uint64_t got;
+	for (uint32_t spins = 0;; ++spins) {
+		asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(p) : "memory");
+		if ((uint32_t)(got >> 32) == epoch)
+			return (uint32_t)got;
+		if (spins > (1u << 24)) // a peer never showed up (~seconds): fail loudly instead of hanging the GPU
+			__trap();
+		if (spins > 16)
+			__nanosleep(32);
+	}
+}
 __device__ __forceinline__ float4 ld_cg4(const float *p) {
 	float4 v;
 	asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -158,6 +172,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	extern __shared__ uint8_t smem_raw[];
 	__shared__ float4 red_sm[3][16][16]; // reduction scratch: [block of the round][partial group][16 x float4 = 64 floats]
 	__shared__ float scratch[16];
+	__shared__ uint32_t peer_counts[NRC_MAX_RANKS];
 	uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	uint8_t *w_sm = smem + kWOff, *act_sm = smem + kActOff, *delta_sm = smem + kDeltaOff;
 	uint64_t *bars = (uint64_t *)(smem + kBarOff);
@@ -529,25 +544,27 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			AdamParams adam = tp.adam;
 			if (adam_mode != 2)
 				adam.use_weights = nullptr;
-			const bool do_adam = adam_mode != 0 && count > 0.0f; // nrc_optimize.comp:33-34 / nrc_train_prepare.comp:22
 			NrcOptimizerState st{};
-			if (do_adam) {
+			if (adam_mode != 0) {
 				const volatile NrcOptimizerState *os = adam.opt_state; // rewritten by the previous batch of this launch
 				NrcOptimizerState old;
 				old.t = os->t, old.beta1_t = os->beta1_t, old.beta2_t = os->beta2_t, old.alpha_t = os->alpha_t, old.alpha_t_1 = os->alpha_t_1;
 				st = advance_state(old);
 			}
+			const uint32_t world = tp.comm.world, me = tp.comm.rank, epoch = tp.comm.epoch_base + b, parity = epoch & 1u;
 			// The 20 736 floats are cut in blocks of 64; CTA c owns blocks c, c + grid, ... and handles up to three of them
 			// per round. Per block: 16 threads x float4 cover the 64 floats of one partial, 16 groups of them take the
 			// partials g, g + 16, g + 32, ... (all loads in flight at once), and the 16 group sums are combined by a
 			// fixed binary tree. Every order is fixed => bit-reproducible.
 			const uint32_t lane16 = threadIdx.x & 15u, grp = (threadIdx.x >> 4) & 15u;
+			bool any_adam = false;
 			for (uint32_t blk0 = blockIdx.x; blk0 < kReduceBlocks; blk0 += 3 * gridDim.x) {
 				// the optimizer entry of "my" element of this round is independent of the sums: fetch it first
 				const uint32_t my_blk = blk0 + (threadIdx.x >> 6) * gridDim.x, my_i = my_blk * 64 + (threadIdx.x & 63u);
-				const bool mine = threadIdx.x < 192 && my_blk < kReduceBlocks && my_i < tp.limit;
+				const bool mine_blk = threadIdx.x < 192 && my_blk < kReduceBlocks, mine = mine_blk && my_i < tp.limit;
+				float sum = 0.0f;
 				NrcOptimizerEntry my_entry{};
-				if (mine && do_adam && my_i < NRC_WEIGHT_COUNT) { // (L2 read: rewritten by another SM earlier in this launch)
+				if (mine && adam_mode != 0 && my_i < NRC_WEIGHT_COUNT) { // (L2 read: rewritten by another SM earlier in this launch)
 					const float4 ev = ld_cg4((const float *)(adam.entries + my_i));
 					my_entry.m = ev.x, my_entry.v = ev.y, my_entry.weight = ev.z, my_entry.ema_weight = ev.w;
 				}
@@ -574,7 +591,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 				}
 				NRC_GTRACE(0x51);
 				__syncthreads();
-				if (mine) {
+				if (mine_blk) {
 					const float *col = &red_sm[threadIdx.x >> 6][0][(threadIdx.x & 63u) >> 2].x + (threadIdx.x & 3u);
 					float t[16];
 #pragma unroll
@@ -586,10 +603,44 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 						for (int k = 0; k < w; ++k)
 							t[k] = t[k] + t[k + w];
 					NRC_GTRACE(0x52);
-					const float sum = t[0];
+					sum = t[0];
+				}
+				float total_count = count;
+				if (world > 1) {
+					// ---- all-reduce over NVLink, fused: push {value, epoch} words into every peer's inbox, spin on the
+					// peers' words in my own inbox, add in rank order (identical operands in identical order on every rank)
+					const size_t dslot = (size_t)parity * NRC_MAX_RANKS * NRC_GRAD_STRIDE, cslot = kCommDataWords + (size_t)parity * NRC_MAX_RANKS * kReduceBlocks;
+					const uint64_t tag = (uint64_t)epoch << 32;
+					if (mine_blk)
+						for (uint32_t r = 0; r < world; ++r)
+							if (r != me)
+								st_peer(tp.comm.inbox[r] + dslot + (size_t)me * NRC_GRAD_STRIDE + my_i, tag | __float_as_uint(sum));
+					if (threadIdx.x >= 192 && threadIdx.x < 192 + NRC_MAX_RANKS) { // one thread per peer: the record counts
+						const uint32_t r = threadIdx.x - 192;
+						uint32_t peer_count = 0;
+						if (r < world && r != me) {
+							st_peer(tp.comm.inbox[r] + cslot + (size_t)me * kReduceBlocks + blk0, tag | __float_as_uint(count));
+							peer_count = wait_peer(tp.comm.inbox[me] + cslot + (size_t)r * kReduceBlocks + blk0, epoch);
+						}
+						peer_counts[r] = peer_count;
+					}
+					if (mine_blk) {
+						float tot = 0.0f;
+						for (uint32_t r = 0; r < world; ++r)
+							tot += r == me ? sum : __uint_as_float(wait_peer(tp.comm.inbox[me] + dslot + (size_t)r * NRC_GRAD_STRIDE + my_i, epoch));
+						sum = tot;
+					}
+					__syncthreads();
+					total_count = 0.0f;
+					for (uint32_t r = 0; r < world; ++r)
+						total_count += r == me ? count : __uint_as_float(peer_counts[r]); // integers < 2^24: exact
+				}
+				if (mine) {
+					const bool do_adam = adam_mode != 0 && total_count > 0.0f; // nrc_optimize.comp:33-34 / nrc_train_prepare.comp:22
+					any_adam = any_adam || do_adam;
 					tp.gradients[my_i] = tp.accumulate ? tp.gradients[my_i] + sum : sum;
 					if (do_adam && my_i < NRC_WEIGHT_COUNT)
-						adam_update(adam, my_i, my_entry, sum, count, st);
+						adam_update(adam, my_i, my_entry, sum, total_count, st);
 				}
 				__syncthreads();
 			}
@@ -598,7 +649,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 				const uint32_t cc = *p.d_count;
 				*p.d_count = cc < tp.batch_cap ? cc : tp.batch_cap;
 			}
-			if (do_adam)
+			if (adam_mode != 0 && __syncthreads_or(any_adam ? 1 : 0)) // (the batch was not empty; identical on every CTA)
 				publish_state_if_last(adam, st);
 		}
 		NRC_GTRACE(0x54);
