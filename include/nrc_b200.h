@@ -24,6 +24,8 @@
 #define NRC_B200_H
 #include <stdint.h>
 
+#include "nrc_b200_types.h"
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -96,6 +98,31 @@ int nrc_infer_unpacked(nrc_handle_t h, const void *d_records, uint32_t stride_by
 int nrc_infer_scatter_unpacked(nrc_handle_t h, const uint32_t *d_dst, uint32_t dst_stride_bytes, const void *d_records,
                                uint32_t stride_bytes, const uint32_t *d_count, uint64_t max_count, void *d_bias_factor_r,
                                const void *d_factor_gb, uint32_t image_pitch, void *const d_train_records[4], void *stream);
+
+/* ---- the reference's own record formats: NRCEvalRecord / NRCTrainRecord + scene buffers ----
+ * nrc_infer == the nrc_inference.comp pass with the bindings of src/rg/NNInference.cpp:13-48: 20-byte eval records
+ *   (binding 8) + device-resident count (9) + scene buffers / textures (0-7) -> UnpackNRCInput -> encode -> MLP with
+ *   use_weights (10) -> max(y,0) -> scatter into bias_factor_r (11, rgba32f RMW) / factor_gb (12) or into the four
+ *   batch_train_records buffers (13). `scene` is a HOST struct of device pointers.
+ * nrc_infer_packed: same unpack + network on PackedNRCInput words `stride_bytes` apart, outputs max(y,0) as fp16x3.
+ * nrc_train_batch == one NNTrain pass group (clear -> prepare -> gradient -> optimize) on a 40-byte NRCTrainRecord
+ *   buffer (bindings src/rg/NNTrain.cpp:59-66, 91-104): target = record.bias, relative-L2-luminance loss, Adam + EMA.
+ * nrc_train_frame == the frame's four pass groups (src/rg/NRCRenderGraph.cpp:57-70) in ONE kernel launch.
+ * nrc_gradient: gradient + reduction only (for a caller that all-reduces the gradient buffer itself). */
+int nrc_infer(nrc_handle_t h, const void *d_eval_records, const uint32_t *d_count, uint64_t max_count,
+              const NrcScene *scene, void *d_bias_factor_r, const void *d_factor_gb, uint32_t image_pitch,
+              void *const d_train_records[4], void *stream);
+int nrc_infer_packed(nrc_handle_t h, const void *d_packed_inputs, uint32_t stride_bytes, const uint32_t *d_count,
+                     uint64_t max_count, const NrcScene *scene, void *d_outputs_f16vec3, void *stream);
+/* UnpackNRCInput on its own (NRCRecord.glsl:98-125): PackedNRCInput words -> [n][14] fp32 in UnpackedNRCInput order. */
+int nrc_unpack_inputs(const void *d_packed_inputs, uint32_t stride_bytes, uint64_t n, const NrcScene *scene,
+                      float *d_unpacked14, void *stream);
+int nrc_gradient(nrc_handle_t h, const void *d_train_records, uint32_t *d_count, uint32_t max_count,
+                 const NrcScene *scene, void *stream);
+int nrc_train_batch(nrc_handle_t h, const void *d_train_records, uint32_t *d_count, uint32_t max_count,
+                    const NrcScene *scene, int write_use_weights, void *stream);
+int nrc_train_frame(nrc_handle_t h, void *const d_train_records[4], uint32_t *const d_counts[4], uint32_t max_count,
+                    const NrcScene *scene, void *stream);
 
 /* ---- training (NNTrain pass group: clear -> prepare -> gradient -> optimize, src/rg/NNTrain.hpp:95-127) ----
  * nrc_gradient_unpacked: gradient pass + deterministic batch reduction into the gradient buffer (replaces clear +

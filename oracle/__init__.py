@@ -81,6 +81,7 @@ def lib() -> C.CDLL:
         L.nrc_oracle_sgd.argtypes = [_f32p, _f32p, _u16p, C.c_float, C.c_float]
         L.nrc_oracle_scatter.argtypes = [_f32p, _u32p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint32,
                                          C.POINTER(C.c_void_p)]
+        L.nrc_oracle_unpack_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, _f32p]
         _lib = L
     return _lib
 
@@ -239,3 +240,50 @@ def ref_train(weights, inputs, targets16) -> np.ndarray:
     rc = ref().vknrc_ref_train(w, x, t, x.shape[0], dw)
     assert rc == 0
     return dw
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Scene buffers + UnpackNRCInput (shader/src/Scene.glsl:8-71, shader/src/NRCRecord.glsl:98-125)
+# ---------------------------------------------------------------------------------------------------------------------
+MATERIAL_DTYPE = np.dtype([("diffuse", "<f4", 3), ("diffuse_texture_id", "<u4"), ("specular", "<f4", 3), ("specular_texture_id", "<u4"),
+                           ("emission", "<f4", 3), ("emission_texture_id", "<u4"), ("metallic", "<f4"), ("roughness", "<f4"),
+                           ("ior", "<f4"), ("_pad", "<u4")])
+assert MATERIAL_DTYPE.itemsize == 64  # std430 array stride of Scene.glsl's Material
+
+
+class _CTexture(C.Structure):
+    _fields_ = [("texels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
+class _CScene(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("vertex_indices", C.c_void_p), ("texcoords", C.c_void_p), ("texcoord_indices", C.c_void_p),
+                ("materials", C.c_void_p), ("material_ids", C.c_void_p), ("transforms", C.c_void_p), ("textures", C.c_void_p),
+                ("texture_count", C.c_uint32)]
+
+
+class Scene:
+    """Host-side scene in the reference's buffer layouts (numpy arrays, kept alive here)."""
+
+    def __init__(self, vertices, vertex_indices, texcoords, texcoord_indices, materials, material_ids, transforms, textures):
+        self.vertices = np.ascontiguousarray(vertices, np.float32).reshape(-1, 3)
+        self.vertex_indices = np.ascontiguousarray(vertex_indices, np.uint32).reshape(-1, 3)
+        self.texcoords = np.ascontiguousarray(texcoords, np.float32).reshape(-1, 2)
+        self.texcoord_indices = np.ascontiguousarray(texcoord_indices, np.uint32).reshape(-1, 3)
+        self.materials = np.ascontiguousarray(materials, MATERIAL_DTYPE)
+        self.material_ids = np.ascontiguousarray(material_ids, np.uint32)
+        self.transforms = np.ascontiguousarray(transforms, np.float32).reshape(-1, 12)
+        self.textures = [np.ascontiguousarray(t, np.uint8) for t in textures]  # [H, W, 4] sRGB
+        self._ctex = (_CTexture * max(1, len(self.textures)))()
+        for i, t in enumerate(self.textures):
+            self._ctex[i] = _CTexture(t.ctypes.data, t.shape[1], t.shape[0])
+        self._c = _CScene(self.vertices.ctypes.data, self.vertex_indices.ctypes.data, self.texcoords.ctypes.data,
+                          self.texcoord_indices.ctypes.data, self.materials.ctypes.data, self.material_ids.ctypes.data,
+                          self.transforms.ctypes.data, C.addressof(self._ctex), len(self.textures))
+
+
+def unpack(scene: Scene, packed: np.ndarray) -> np.ndarray:
+    """UnpackNRCInput: [n,4] uint32 PackedNRCInput -> [n,14] fp32 (UnpackedNRCInput order)."""
+    pk = np.ascontiguousarray(packed, np.uint32).reshape(-1, 4)
+    out = np.empty((pk.shape[0], 14), np.float32)
+    lib().nrc_oracle_unpack_batch(C.addressof(scene._c), pk.ctypes.data, pk.shape[0], 16, out)
+    return out

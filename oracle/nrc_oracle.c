@@ -442,4 +442,85 @@ void nrc_oracle_scatter(const float *predict, const uint32_t *dst, uint64_t n, f
 	}
 }
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * UnpackNRCInput (shader/src/NRCRecord.glsl:98-125) over the scene buffers of shader/src/Scene.glsl:8-71.
+ * Pointers are HOST pointers here. Texture fetch = what `texture(sampler2D, uv)` does in a compute shader for an
+ * R8G8B8A8_SRGB image with one mip level, VK_FILTER_LINEAR, ADDRESS_MODE_REPEAT: sRGB -> linear per texel, then a
+ * bilinear blend of the 2x2 footprint around uv*size - 0.5 (fp32 weights; the hardware quantises them to 8 bits).
+ * ------------------------------------------------------------------------------------------------------------------ */
+typedef struct { float diffuse[3]; uint32_t diffuse_texture_id; float specular[3]; uint32_t specular_texture_id;
+                 float emission[3]; uint32_t emission_texture_id; float metallic, roughness, ior; uint32_t pad; } NrcOracleMaterial;
+typedef struct { const void *texels; uint32_t width, height; } NrcOracleTexture;
+typedef struct { const float *vertices; const uint32_t *vertex_indices; const float *texcoords; const uint32_t *texcoord_indices;
+                 const NrcOracleMaterial *materials; const uint32_t *material_ids; const float *transforms;
+                 const NrcOracleTexture *textures; uint32_t texture_count; } NrcOracleScene;
+
+static float srgb_to_linear(uint8_t c) {
+	float x = (float)c / 255.0f;
+	return x <= 0.04045f ? x / 12.92f : powf((x + 0.055f) / 1.055f, 2.4f);
+}
+static void sample_texture(const NrcOracleTexture *t, float u, float v, float rgb[3]) {
+	float x = u * (float)t->width - 0.5f, y = v * (float)t->height - 0.5f;
+	float fx = floorf(x), fy = floorf(y), tx = x - fx, ty = y - fy;
+	int w = (int)t->width, h = (int)t->height;
+	int x0 = (int)fx % w, y0 = (int)fy % h;
+	if (x0 < 0) x0 += w;
+	if (y0 < 0) y0 += h;
+	int x1 = (x0 + 1) % w, y1 = (y0 + 1) % h;
+	const uint8_t *p = (const uint8_t *)t->texels;
+	for (int c = 0; c < 3; ++c) {
+		float c00 = srgb_to_linear(p[4 * (y0 * w + x0) + c]), c10 = srgb_to_linear(p[4 * (y0 * w + x1) + c]);
+		float c01 = srgb_to_linear(p[4 * (y1 * w + x0) + c]), c11 = srgb_to_linear(p[4 * (y1 * w + x1) + c]);
+		rgb[c] = (c00 * (1.0f - tx) + c10 * tx) * (1.0f - ty) + (c01 * (1.0f - tx) + c11 * tx) * ty;
+	}
+}
+static void scene_vertex(const NrcOracleScene *sc, uint32_t instance, uint32_t prim, uint32_t k, float out[3]) { /* Scene.glsl:50-53 */
+	const float *v = sc->vertices + 3 * (size_t)sc->vertex_indices[3 * (size_t)prim + k];
+	const float *m = sc->transforms + 12 * (size_t)instance; /* 3 columns of vec4; vec4(v,1) * M -> dot with each column */
+	for (int j = 0; j < 3; ++j)
+		out[j] = v[0] * m[4 * j] + v[1] * m[4 * j + 1] + v[2] * m[4 * j + 2] + m[4 * j + 3];
+}
+void nrc_oracle_unpack_input(const NrcOracleScene *sc, const uint32_t packed[4], float out14[14]) {
+	uint32_t prim = packed[0], instance = packed[1] & 0x7FFFFFFFu;
+	int flip = (int)(packed[1] >> 31);
+	float v[3][3], tc[3][2];
+	for (uint32_t k = 0; k < 3; ++k) {
+		scene_vertex(sc, instance, prim, k, v[k]);
+		const float *t = sc->texcoords + 2 * (size_t)sc->texcoord_indices[3 * (size_t)prim + k];
+		tc[k][0] = t[0], tc[k][1] = t[1];
+	}
+	float e1[3], e2[3], nrm[3];
+	for (int j = 0; j < 3; ++j)
+		e1[j] = v[1][j] - v[0][j], e2[j] = v[2][j] - v[0][j];
+	nrm[0] = e1[1] * e2[2] - e1[2] * e2[1], nrm[1] = e1[2] * e2[0] - e1[0] * e2[2], nrm[2] = e1[0] * e2[1] - e1[1] * e2[0];
+	float inv = 1.0f / sqrtf(nrm[0] * nrm[0] + nrm[1] * nrm[1] + nrm[2] * nrm[2]);
+	for (int j = 0; j < 3; ++j)
+		nrm[j] = flip ? -(nrm[j] * inv) : nrm[j] * inv;
+	float by = (float)(packed[2] & 0xFFFFu) / 65535.0f, bz = (float)(packed[2] >> 16) / 65535.0f, bx = 1.0f - by - bz; /* :111-112 */
+	for (int j = 0; j < 3; ++j)
+		out14[j] = v[0][j] * bx + v[1][j] * by + v[2][j] * bz;
+	out14[3] = (float)(packed[3] & 0xFFFFu) / 65535.0f, out14[4] = (float)(packed[3] >> 16) / 65535.0f; /* :118 */
+	/* NRCSphEncode, :47-49 */
+	out14[5] = (nrm[0] == 0.0f && nrm[1] == 0.0f) ? 0.5f : 0.5f + atan2f(nrm[1], nrm[0]) / (2.0f * 3.14159265358979323846f);
+	out14[6] = acosf(fminf(fmaxf(nrm[2], -1.0f), 1.0f)) / 3.14159265358979323846f;
+	const NrcOracleMaterial *m = sc->materials + sc->material_ids[prim];
+	out14[7] = m->roughness;
+	float u = tc[0][0] * bx + tc[1][0] * by + tc[2][0] * bz, w = tc[0][1] * bx + tc[1][1] * by + tc[2][1] * bz;
+	if (m->diffuse_texture_id == 0xFFFFFFFFu)
+		memcpy(out14 + 8, m->diffuse, 12);
+	else
+		sample_texture(sc->textures + m->diffuse_texture_id, u, w, out14 + 8);
+	if (m->specular_texture_id == 0xFFFFFFFFu)
+		memcpy(out14 + 11, m->specular, 12);
+	else
+		sample_texture(sc->textures + m->specular_texture_id, u, w, out14 + 11);
+}
+void nrc_oracle_unpack_batch(const NrcOracleScene *sc, const uint8_t *packed, uint64_t n, uint32_t stride_bytes, float *out14) {
+	for (uint64_t i = 0; i < n; ++i) {
+		uint32_t pk[4];
+		memcpy(pk, packed + i * stride_bytes, 16);
+		nrc_oracle_unpack_input(sc, pk, out14 + 14 * i);
+	}
+}
+
 int nrc_oracle_weight_count(void) { return NRC_WEIGHTS; }

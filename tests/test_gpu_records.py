@@ -1,0 +1,199 @@
+"""GPU parity of the reference's own record formats (run with -m gpu): 16-byte PackedNRCInput inside 20-byte NRCEvalRecord
+/ 40-byte NRCTrainRecord arrays, unpacked on the fly from scene buffers (UnpackNRCInput, shader/src/NRCRecord.glsl:98-125
+over shader/src/Scene.glsl:8-71) - against the CPU restatement in oracle/. The reference ships no fixtures for this step
+and its GLSL cannot run here, so this row is pinned by the restatement alone."""
+import numpy as np
+import pytest
+
+from util import GRAD_REL_TOL, he_weights, layer_rel_err, make_scene, out_err, random_packed_inputs
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+@pytest.fixture(scope="module")
+def nrc():
+    import vknrc_b200
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    vknrc_b200.lib()
+    return vknrc_b200
+
+
+@pytest.fixture(scope="module")
+def oracle_mod():
+    import oracle
+    return oracle
+
+
+@pytest.fixture()
+def state(nrc):
+    st = nrc.NrcState(0, (64, 48), seed=3)
+    yield st
+    st.close()
+
+
+def upload_scene(nrc, sc):
+    return nrc.DeviceScene(sc.vertices, sc.vertex_indices, sc.texcoords, sc.texcoord_indices, sc.materials, sc.material_ids, sc.transforms,
+                           sc.textures)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_unpack_matches_oracle(nrc, oracle_mod):
+    sc = make_scene(5)
+    dsc = upload_scene(nrc, sc)
+    for n in (1, 255, 5000):
+        pk = random_packed_inputs(6, n, sc)
+        got = nrc.unpack_inputs(dev(pk), dsc).cpu().numpy()
+        ref = oracle_mod.unpack(sc, pk)
+        # integer decodes are exact; gathers + fp32 arithmetic differ by FMA contraction and libm ulps only
+        assert np.array_equal(got[:, 3:5], ref[:, 3:5])                      # scattered dir: unorm16 decode, bit-exact
+        assert np.array_equal(got[:, 7], ref[:, 7])                          # roughness: a plain gather
+        assert np.abs(got[:, :3] - ref[:, :3]).max() <= 4e-6                 # position (|p| < 4)
+        assert np.abs(got[:, 5:7] - ref[:, 5:7]).max() <= 2e-6               # spherical normal
+        assert np.abs(got[:, 8:] - ref[:, 8:]).max() <= 2e-5                 # diffuse / specular incl. sRGB texture fetches
+        # (a 1-ulp difference in uv is scaled by the texture size times the texel contrast; fp16 features resolve 5e-4)
+    # strided source: the PackedNRCInput sits at byte 4 of a 20-byte NRCEvalRecord and byte 24 of a 40-byte NRCTrainRecord
+    pk = random_packed_inputs(7, 300, sc)
+    ev = np.zeros(300, nrc.EVAL_RECORD_DTYPE)
+    ev["packed_input"] = np.ascontiguousarray(pk).view(nrc.EVAL_RECORD_DTYPE["packed_input"]).reshape(300)
+    d_ev = dev(ev.view(np.uint8).reshape(-1))
+    got = nrc.unpack_inputs(d_ev[4:], dsc, stride_bytes=20, n=300).cpu().numpy()
+    assert np.abs(got - oracle_mod.unpack(sc, pk)).max() <= 2e-5
+
+
+def test_infer_packed_matches_oracle(nrc, oracle_mod, state):
+    sc = make_scene(11)
+    dsc = upload_scene(nrc, sc)
+    w32 = he_weights(12)
+    state.set_weights(w32)
+    n = 3001
+    pk = random_packed_inputs(13, n, sc)
+    y = state.infer_packed(dev(pk), dsc).float().cpu().numpy()
+    ref = oracle_mod.evaluate(w32.astype(np.float16), oracle_mod.encode(oracle_mod.unpack(sc, pk)), oracle_mod.ACC_FP32, clamp=True)
+    assert out_err(y, ref.astype(np.float32)) <= 1.0
+
+
+def test_nrc_infer_eval_records_scatter(nrc, oracle_mod, state):
+    """The full nrc_inference.comp pass on NRCEvalRecord[]: device count, invalid / screen / train destinations."""
+    sc = make_scene(21)
+    dsc = upload_scene(nrc, sc)
+    w32 = he_weights(22)
+    state.set_weights(w32)
+    W, H, n = 64, 48, 2500
+    rng = np.random.default_rng(23)
+    pk = random_packed_inputs(24, n, sc)
+    dst = np.zeros(n, np.uint32)
+    perm = rng.permutation(W * H)[:n]  # distinct pixels: the screen RMW has no ordering between duplicates
+    kind = rng.integers(0, 10, n)
+    tr_cursor = [0, 0, 0, 0]
+    for i in range(n):
+        if kind[i] == 0:
+            dst[i] = 0xFFFFFFFF
+        elif kind[i] <= 6:
+            dst[i] = oracle_mod.dst_screen(int(perm[i] % W), int(perm[i] // W))
+        else:  # disjoint [l, r] ranges per batch (as the path tracer emits them, path_tracer.comp:343-371)
+            b = int(rng.integers(0, 4))
+            ln = int(rng.integers(1, 5))
+            if tr_cursor[b] + ln > 1024:
+                dst[i] = 0xFFFFFFFF
+                continue
+            dst[i] = oracle_mod.dst_train(b, tr_cursor[b], tr_cursor[b] + ln - 1)
+            tr_cursor[b] += ln
+    ev = np.zeros(n + 50, nrc.EVAL_RECORD_DTYPE)  # 50 records past the device count must be ignored
+    ev["dst"][:n] = dst
+    ev["dst"][n:] = oracle_mod.dst_screen(0, 0)
+    ev["packed_input"][:n] = np.ascontiguousarray(pk).view(nrc.EVAL_RECORD_DTYPE["packed_input"]).reshape(n)
+    ev["packed_input"][n:] = ev["packed_input"][0]
+    bf = rng.uniform(0, 1, (H, W, 4)).astype(np.float32)
+    gb = rng.uniform(0, 1, (H, W, 2)).astype(np.float32)
+    tr = [np.zeros(1024, nrc.TRAIN_RECORD_DTYPE) for _ in range(4)]
+    for t in tr:
+        t["bias"], t["factor"] = rng.uniform(0, 1, (1024, 3)), rng.uniform(0, 1, (1024, 3))
+    d_bf, d_gb = dev(bf), dev(gb)
+    d_tr = [dev(t.view(np.uint8).reshape(-1)) for t in tr]
+    count = torch.tensor([n], dtype=torch.int32, device="cuda")
+    state.infer(dev(ev.view(np.uint8).reshape(-1)), count, dsc, d_bf, d_gb, W, d_tr, max_count=n + 50)
+    g_bf = d_bf.cpu().numpy()
+    g_tr = [t.cpu().numpy().view(nrc.TRAIN_RECORD_DTYPE) for t in d_tr]
+    # oracle: predictions through the restated unpack + encode + network, then the restated scatter
+    pred = oracle_mod.evaluate(w32.astype(np.float16), oracle_mod.encode(oracle_mod.unpack(sc, pk)), oracle_mod.ACC_FP32, clamp=True).astype(np.float32)
+    exp_bf = bf.copy()
+    exp_tr = [t.copy().view(np.float32).reshape(-1, 10) for t in tr]  # 40-byte records as 10 floats: bias, factor, packed input
+    oracle_mod.scatter(pred, dst, exp_bf, gb, W, exp_tr)
+    scale = np.abs(pred).max()
+    assert np.abs(g_bf - exp_bf).max() <= 1e-2 * scale
+    untouched = np.ones(W * H, bool)
+    for i in range(n):
+        if dst[i] != 0xFFFFFFFF and (dst[i] & 1) == 0:
+            untouched[perm[i]] = False
+    assert np.array_equal(g_bf.reshape(-1, 4)[untouched], bf.reshape(-1, 4)[untouched])  # bit-exact indexing: nothing else moved
+    for b in range(4):
+        got = g_tr[b].view(np.float32).reshape(-1, 10)
+        assert np.abs(got[:, :6] - exp_tr[b][:, :6]).max() <= 1e-2 * scale
+        assert np.array_equal(got[tr_cursor[b]:].view(np.uint32), exp_tr[b][tr_cursor[b]:].view(np.uint32))  # rows past the ranges untouched
+        assert np.array_equal(g_tr[b]["packed_input"], tr[b]["packed_input"])
+
+
+def test_train_records_match_oracle_and_unpacked_path(nrc, oracle_mod, state):
+    sc = make_scene(31)
+    dsc = upload_scene(nrc, sc)
+    w32 = he_weights(32)
+    n = 4000
+    pk = random_packed_inputs(33, n, sc)
+    rng = np.random.default_rng(34)
+    rec = np.zeros(n, nrc.TRAIN_RECORD_DTYPE)
+    rec["bias"], rec["factor"] = rng.uniform(0, 1, (n, 3)), rng.uniform(0, 1, (n, 3))
+    rec["packed_input"] = np.ascontiguousarray(pk).view(nrc.TRAIN_RECORD_DTYPE["packed_input"]).reshape(n)
+    d_rec = dev(rec.view(np.uint8).reshape(-1))
+    state.set_weights(w32)
+    state.gradient(d_rec, dsc)
+    g = state.download()["gradients"]
+    # The gather itself is checked in test_unpack_matches_oracle. Its fp32 ulp differences (FMA contraction, libm) are
+    # amplified 2048x by the top frequency octave, so the NETWORK is compared on the device's own unpacked values.
+    unp = nrc.unpack_inputs(d_rec[24:], dsc, stride_bytes=40, n=n).cpu().numpy()
+    assert np.abs(unp - oracle_mod.unpack(sc, pk)).max() <= 2e-5
+    gref = oracle_mod.gradient(w32.astype(np.float16), oracle_mod.encode(unp), np.ascontiguousarray(rec["bias"]), oracle_mod.LOSS_RELATIVE_L2_LUMINANCE,
+                               1.0, oracle_mod.ACC_FP32)
+    assert max(layer_rel_err(g[:nrc.WEIGHT_COUNT], gref)) <= GRAD_REL_TOL
+    assert g[nrc.GRAD_COUNT_SLOT] == n
+    # the same batch through the 14-float entry point (inputs unpacked by the oracle): same network, same optimizer
+    state.set_weights(w32)
+    state.train_batch(d_rec, dsc, write_use_weights=True)
+    a = state.download()
+    state.set_weights(w32)
+    state.train_batch_unpacked(dev(unp), dev(np.ascontiguousarray(rec["bias"])), write_use_weights=True)
+    b = state.download()
+    assert np.abs(a["weights"].astype(np.float32) - b["weights"].astype(np.float32)).max() <= 2e-3
+    assert a["optimizer_state"] == b["optimizer_state"]
+
+
+def test_train_frame_records_equals_four_batches(nrc, state):
+    sc = make_scene(41)
+    dsc = upload_scene(nrc, sc)
+    w32 = he_weights(42)
+    rng = np.random.default_rng(43)
+    nb = 2048
+    recs = []
+    for b in range(4):
+        r = np.zeros(nb, nrc.TRAIN_RECORD_DTYPE)
+        r["bias"], r["factor"] = rng.uniform(0, 1, (nb, 3)), rng.uniform(0, 1, (nb, 3))
+        r["packed_input"] = np.ascontiguousarray(random_packed_inputs(50 + b, nb, sc)).view(nrc.TRAIN_RECORD_DTYPE["packed_input"]).reshape(nb)
+        recs.append(dev(r.view(np.uint8).reshape(-1)))
+    res = []
+    for frame in (True, False):
+        state.set_weights(w32)
+        counts = [torch.tensor([c], dtype=torch.int32, device="cuda") for c in (nb, 100, 0, 5000)]
+        if frame:
+            state.train_frame(recs, dsc, counts, max_count=nb)
+        else:
+            for b in range(4):
+                state.train_batch(recs[b], dsc, count=counts[b], max_count=nb, write_use_weights=(b == 3))
+        res.append((state.download(), [int(c.item()) for c in counts]))
+    (a, ca), (b, cb) = res
+    assert ca == cb == [nb, 100, 0, nb]
+    for k in ("weights", "use_weights", "optimizer_entries", "gradients"):
+        assert np.array_equal(np.ascontiguousarray(a[k]).view(np.uint8), np.ascontiguousarray(b[k]).view(np.uint8)), k
+    assert a["optimizer_state"]["t"] == 3

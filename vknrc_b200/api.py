@@ -31,6 +31,46 @@ TRAIN_RECORD_DTYPE = np.dtype([("bias", "<f4", 3), ("factor", "<f4", 3), ("packe
 assert EVAL_RECORD_DTYPE.itemsize == 20 and TRAIN_RECORD_DTYPE.itemsize == 40
 
 
+MATERIAL_DTYPE = np.dtype([("diffuse", "<f4", 3), ("diffuse_texture_id", "<u4"), ("specular", "<f4", 3), ("specular_texture_id", "<u4"),
+                           ("emission", "<f4", 3), ("emission_texture_id", "<u4"), ("metallic", "<f4"), ("roughness", "<f4"),
+                           ("ior", "<f4"), ("_pad", "<u4")])  # shader/src/Scene.glsl:12-20, 64 B std430 stride
+assert MATERIAL_DTYPE.itemsize == 64
+
+
+class nrc_texture_t(C.Structure):  # include/nrc_b200_types.h NrcTexture
+    _fields_ = [("texels_rgba8_srgb", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
+class nrc_scene_t(C.Structure):  # include/nrc_b200_types.h NrcScene (device pointers)
+    _fields_ = [("vertices", C.c_void_p), ("vertex_indices", C.c_void_p), ("texcoords", C.c_void_p), ("texcoord_indices", C.c_void_p),
+                ("materials", C.c_void_p), ("material_ids", C.c_void_p), ("transforms", C.c_void_p), ("textures", C.c_void_p),
+                ("texture_count", C.c_uint32)]
+
+
+class DeviceScene:
+    """Uploads scene buffers given in the reference's layouts (numpy arrays; see shader/src/Scene.glsl:8-71) and holds
+    the NrcScene struct of device pointers that the record-format entry points take."""
+
+    def __init__(self, vertices, vertex_indices, texcoords, texcoord_indices, materials, material_ids, transforms, textures, device=0):
+        import torch
+        dev = f"cuda:{device}"
+
+        def up(a, dt):
+            return torch.from_numpy(np.ascontiguousarray(a, dt).view(np.uint8).reshape(-1)).to(dev)
+        self._keep = {"vertices": up(vertices, np.float32), "vertex_indices": up(vertex_indices, np.uint32), "texcoords": up(texcoords, np.float32),
+                      "texcoord_indices": up(texcoord_indices, np.uint32), "materials": up(materials, MATERIAL_DTYPE),
+                      "material_ids": up(material_ids, np.uint32), "transforms": up(transforms, np.float32)}
+        self._tex = [up(t, np.uint8) for t in textures]
+        table = (nrc_texture_t * max(1, len(textures)))()
+        for i, t in enumerate(textures):
+            table[i] = nrc_texture_t(self._tex[i].data_ptr(), t.shape[1], t.shape[0])
+        self._table = torch.from_numpy(np.frombuffer(bytes(table), np.uint8).copy()).to(dev)
+        k = self._keep
+        self.c = nrc_scene_t(k["vertices"].data_ptr(), k["vertex_indices"].data_ptr(), k["texcoords"].data_ptr(), k["texcoord_indices"].data_ptr(),
+                             k["materials"].data_ptr(), k["material_ids"].data_ptr(), k["transforms"].data_ptr(), self._table.data_ptr(),
+                             len(textures))
+
+
 class NrcError(RuntimeError):
     pass
 
@@ -80,6 +120,13 @@ SIGNATURES = {
                                            C.c_int, C.c_void_p]),
     "nrc_train_frame_unpacked": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.c_uint32, C.POINTER(C.c_void_p), C.c_uint32,
                                            C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p]),
+    "nrc_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                            C.POINTER(C.c_void_p), C.c_void_p]),
+    "nrc_infer_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nrc_unpack_inputs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nrc_gradient": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
+    "nrc_train_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]),
+    "nrc_train_frame": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p, C.c_void_p]),
     "nrc_comm_handle_bytes": (C.c_uint32, []),
     "nrc_comm_init": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]),
     "nrc_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
@@ -145,6 +192,15 @@ def mlp_gradient_encoded(weights, dw, inputs, targets):
     """launchKernel("train_32.spv", ..., weights, dw, inputs, targets) (test/main.cpp:180-181); dw accumulates."""
     _check(lib().nrc_mlp_gradient_encoded(_ptr(weights), _ptr(dw), _ptr(inputs), _ptr(targets), inputs.shape[0], _stream()))
     return dw
+
+
+def unpack_inputs(packed_inputs, scene: "DeviceScene", stride_bytes: int = 16, n=None):
+    """UnpackNRCInput (NRCRecord.glsl:98-125) as a kernel of its own: -> [n,14] fp32."""
+    import torch
+    n = packed_inputs.numel() * packed_inputs.element_size() // stride_bytes if n is None else n
+    out = torch.empty((n, 14), dtype=torch.float32, device=packed_inputs.device)
+    _check(lib().nrc_unpack_inputs(_ptr(packed_inputs), stride_bytes, n, C.byref(scene.c), _ptr(out), _stream()))
+    return out
 
 
 class NrcState:
@@ -284,6 +340,36 @@ class NrcState:
         tgs = (C.c_void_p * 4)(*[_ptr(t) for t in targets])
         cns = (C.c_void_p * 4)(*[_ptr(t) for t in counts]) if counts is not None else None
         _check(lib().nrc_train_frame_unpacked(self._h, ins, input_stride, tgs, target_stride, cns, n, _stream()))
+
+    # ---- the reference's own record formats (NRCEvalRecord 20 B / NRCTrainRecord 40 B) + scene gather
+    def infer(self, eval_records, count, scene: "DeviceScene", bias_factor_r, factor_gb, image_pitch, train_records, max_count=None):
+        """nrc_inference.comp with the bindings of src/rg/NNInference.cpp:13-48. eval_records: uint8/uint32 tensor of 20 B records."""
+        n = eval_records.numel() * eval_records.element_size() // 20 if max_count is None else max_count
+        ptrs = (C.c_void_p * 4)(*[_ptr(t) for t in train_records])
+        _check(lib().nrc_infer(self._h, _ptr(eval_records), _ptr(count), n, C.byref(scene.c), _ptr(bias_factor_r), _ptr(factor_gb), image_pitch,
+                               ptrs, _stream()))
+
+    def infer_packed(self, packed_inputs, scene: "DeviceScene", count=None, outputs=None, stride_bytes: int = 16, max_count=None):
+        import torch
+        n = packed_inputs.numel() * packed_inputs.element_size() // stride_bytes if max_count is None else max_count
+        if outputs is None:
+            outputs = torch.empty((n, 3), dtype=torch.float16, device=packed_inputs.device)
+        _check(lib().nrc_infer_packed(self._h, _ptr(packed_inputs), stride_bytes, _ptr(count), n, C.byref(scene.c), _ptr(outputs), _stream()))
+        return outputs
+
+    def gradient(self, train_records, scene: "DeviceScene", count=None, max_count=None):
+        n = train_records.numel() * train_records.element_size() // 40 if max_count is None else max_count
+        _check(lib().nrc_gradient(self._h, _ptr(train_records), _ptr(count), n, C.byref(scene.c), _stream()))
+
+    def train_batch(self, train_records, scene: "DeviceScene", count=None, max_count=None, write_use_weights=True):
+        n = train_records.numel() * train_records.element_size() // 40 if max_count is None else max_count
+        _check(lib().nrc_train_batch(self._h, _ptr(train_records), _ptr(count), n, C.byref(scene.c), int(write_use_weights), _stream()))
+
+    def train_frame(self, train_records, scene: "DeviceScene", counts=None, max_count=None):
+        n = train_records[0].numel() * train_records[0].element_size() // 40 if max_count is None else max_count
+        recs = (C.c_void_p * 4)(*[_ptr(t) for t in train_records])
+        cns = (C.c_void_p * 4)(*[_ptr(t) for t in counts]) if counts is not None else None
+        _check(lib().nrc_train_frame(self._h, recs, cns, n, C.byref(scene.c), _stream()))
 
     # ---- multi-GPU (one process per GPU)
     def comm_connect(self, group=None):

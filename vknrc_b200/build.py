@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnrc_b200.so")
 SOURCES = ["nrc_infer.cu", "nrc_train.cu", "nrc_state.cu"]
-HEADERS = ["sm100_ptx.cuh", "nrc_config.h", "nrc_kernels.h", "nrc_encode.cuh", "nrc_state.hpp", "../../include/nrc_b200.h"]
+HEADERS = ["sm100_ptx.cuh", "nrc_config.h", "nrc_kernels.h", "nrc_encode.cuh", "nrc_unpack.cuh", "nrc_state.hpp", "../../include/nrc_b200.h"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]
 

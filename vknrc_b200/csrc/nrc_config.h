@@ -30,30 +30,4 @@
 #define NRC_GRAD_COUNT_SLOT (NRC_WEIGHT_COUNT + 1) /* number of records that contributed (as float, exact < 2^24) */
 #define NRC_GRAD_STRIDE (NRC_WEIGHT_COUNT + 64)    /* 20736 */
 
-#ifdef __cplusplus
-extern "C" {
-#endif
-typedef struct NrcPackedInput { /* NRCRecord.glsl:6-10 */
-	uint32_t primitive_id, flip_bit_instance_id, barycentric_2x16U, scattered_dir_2x16U;
-} NrcPackedInput;
-typedef struct NrcEvalRecord { /* NRCRecord.glsl:12-18, 20 B */
-	uint32_t dst;
-	NrcPackedInput packed_input;
-} NrcEvalRecord;
-typedef struct NrcTrainRecord { /* NRCRecord.glsl:35-38, 40 B */
-	float bias_r, bias_g, bias_b, factor_r, factor_g, factor_b;
-	NrcPackedInput packed_input;
-} NrcTrainRecord;
-typedef struct NrcUnpackedInput { /* NRCRecord.glsl:40-45 flattened, 56 B */
-	float position[3], scattered_dir[2], normal[2], roughness, diffuse[3], specular[3];
-} NrcUnpackedInput;
-typedef struct NrcOptimizerState { /* src/VkNRCState.cpp:25-28, 20 B */
-	uint32_t t;
-	float beta1_t, beta2_t, alpha_t, alpha_t_1;
-} NrcOptimizerState;
-typedef struct NrcOptimizerEntry { /* src/VkNRCState.cpp:29-31, 16 B */
-	float m, v, weight, ema_weight;
-} NrcOptimizerEntry;
-#ifdef __cplusplus
-}
-#endif
+#include "../../include/nrc_b200_types.h" /* record / optimizer / scene structs shared with the public C ABI */

@@ -16,6 +16,7 @@
 // mbarrier d_full[slot] (tcgen05.commit -> epilogue) and in_full[slot][2] (TMA -> layer-0 MMA).
 #include "nrc_kernels.h"
 #include "nrc_encode.cuh"
+#include "nrc_unpack.cuh"
 
 using namespace sm100;
 
@@ -183,9 +184,13 @@ __global__ void __launch_bounds__(NT * 128, 1)
 		const bool valid = gi < n;
 		if (IN_MODE != NRC_IN_ENCODED) {
 			uint32_t o[32];
-			if (IN_MODE == NRC_IN_UNPACKED) {
+			if (IN_MODE == NRC_IN_UNPACKED || IN_MODE == NRC_IN_PACKED) {
 				float in[14];
-				if (valid) {
+				if (valid && IN_MODE == NRC_IN_PACKED) {
+					uint32_t pk[4];
+					load_packed_input(p.in, gi, p.in_stride_bytes, pk);
+					unpack_nrc_input(p.scene, pk, in);
+				} else if (valid) {
 					const float2 *src = (const float2 *)((const uint8_t *)p.in + gi * p.in_stride_bytes);
 #pragma unroll
 					for (int i = 0; i < 7; ++i) {
@@ -323,6 +328,28 @@ template <int NT, int IN_MODE> static cudaError_t launch(const InferParams &p, c
 	return cudaGetLastError();
 }
 
+// Stand-alone UnpackNRCInput (NRCRecord.glsl:98-125): [n] PackedNRCInput -> [n][14] fp32. The fused kernels above never
+// materialise this; it exists for parity checks of the gather and as the HBM-bound record-streaming stage on its own.
+__global__ void __launch_bounds__(256) nrc_unpack_kernel(const void *packed, uint32_t stride_bytes, uint64_t n, const NrcScene scene, float *out14) {
+	const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n)
+		return;
+	uint32_t pk[4];
+	float in[14];
+	load_packed_input(packed, i, stride_bytes, pk);
+	unpack_nrc_input(scene, pk, in);
+	float2 *dst = (float2 *)(out14 + 14 * i);
+#pragma unroll
+	for (int k = 0; k < 7; ++k)
+		dst[k] = make_float2(in[2 * k], in[2 * k + 1]);
+}
+cudaError_t launch_unpack(const void *packed, uint32_t stride_bytes, uint64_t n, const NrcScene &scene, float *out14, cudaStream_t stream) {
+	if (n == 0)
+		return cudaSuccess;
+	nrc_unpack_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(packed, stride_bytes, n, scene, out14);
+	return cudaGetLastError();
+}
+
 cudaError_t launch_infer(const InferParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream) {
 	if (p.n == 0)
 		return cudaSuccess;
@@ -334,6 +361,8 @@ cudaError_t launch_infer(const InferParams &p, const CUtensorMap &tm_w, const CU
 		return launch<NT, NRC_IN_UNPACKED>(p, tm_w, tm_in, sms, stream);
 	case NRC_IN_IMAGE_GRID:
 		return launch<NT, NRC_IN_IMAGE_GRID>(p, tm_w, tm_in, sms, stream);
+	case NRC_IN_PACKED:
+		return launch<NT, NRC_IN_PACKED>(p, tm_w, tm_in, sms, stream);
 	}
 	return cudaErrorInvalidValue;
 }

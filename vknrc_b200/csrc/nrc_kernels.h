@@ -17,7 +17,8 @@ enum InMode : int {
 	NRC_IN_ENCODED = 0,   // [n][64] fp16, test/evaluate_NV.comp:18-21
 	NRC_IN_UNPACKED = 1,  // [n] NrcUnpackedInput-shaped records (14 fp32 at a caller-given stride), encode fused
 	NRC_IN_IMAGE_GRID = 2, // learn-an-image inference: uv from the pixel index (inference.comp:33-34)
-	NRC_IN_IMAGE_RANDOM = 3 // learn-an-image training: uv from pcg2d(seed + gid) (gradient.comp:47-48)
+	NRC_IN_IMAGE_RANDOM = 3, // learn-an-image training: uv from pcg2d(seed + gid) (gradient.comp:47-48)
+	NRC_IN_PACKED = 4      // [n] PackedNRCInput (16 B inside 20 B eval / 40 B train records): UnpackNRCInput + encode fused
 };
 enum OutMode : int {
 	NRC_OUT_F16VEC3 = 0, // [n][3] fp16, test/evaluate_NV.comp:29-30
@@ -30,8 +31,9 @@ struct InferParams {
 	uint64_t n;               // number of queries (upper bound when d_count != nullptr)
 	const uint32_t *d_count;  // optional device-resident count
 	int in_mode, out_mode, clamp_output;
-	const void *in;           // NRC_IN_UNPACKED: first record's 14 floats
-	uint32_t in_stride_bytes; // NRC_IN_UNPACKED: bytes between records (56 for a packed array)
+	const void *in;           // NRC_IN_UNPACKED: first record's 14 floats; NRC_IN_PACKED: first record's PackedNRCInput
+	uint32_t in_stride_bytes; // bytes between records (56 for an array of unpacked inputs, 20 for NRCEvalRecord)
+	NrcScene scene;           // NRC_IN_PACKED: the buffers UnpackNRCInput gathers from
 	uint32_t image_width;     // NRC_IN_IMAGE_GRID
 	void *out;                // F16VEC3 / RGBA8
 	const uint32_t *dst;      // SCATTER: eval-record dst words
@@ -47,8 +49,9 @@ struct GradParams {
 	uint32_t *d_count;       // optional device-resident count (read clamped to n; written back clamped to batch_cap)
 	int in_mode, loss_kind;
 	float loss_scale;
-	const void *in;          // ENCODED: unused (TMA); UNPACKED: 14 floats per record at in_stride_bytes
+	const void *in;          // ENCODED: unused (TMA); UNPACKED: 14 floats per record at in_stride_bytes; PACKED: PackedNRCInput
 	uint32_t in_stride_bytes;
+	NrcScene scene;          // PACKED: the buffers UnpackNRCInput gathers from
 	const void *target;      // ENCODED: [n][3] fp16 (test/train_NV.comp:11-16); UNPACKED: 3 fp32 at target_stride_bytes
 	uint32_t target_stride_bytes;
 	int target_is_f16;
@@ -114,6 +117,7 @@ struct SgdParams { // mlp_learning_an_image/optimize.comp:21-29
 cudaError_t launch_infer(const InferParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream);
 // cooperative launch: grid = min(#tiles of the largest batch, #SMs) CTAs, all co-resident
 cudaError_t launch_train(const TrainParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream);
+cudaError_t launch_unpack(const void *packed, uint32_t stride_bytes, uint64_t n, const NrcScene &scene, float *out14, cudaStream_t stream);
 cudaError_t launch_adam(const AdamParams &p, cudaStream_t stream);
 cudaError_t launch_sgd(const SgdParams &p, cudaStream_t stream);
 uint32_t gradient_max_partials(int sms);

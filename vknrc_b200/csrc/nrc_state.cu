@@ -2,6 +2,7 @@
 #include "nrc_state.hpp"
 
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <mutex>
@@ -477,6 +478,116 @@ int nrc_infer_scatter_unpacked(nrc_handle_t h, const uint32_t *d_dst, uint32_t d
 	for (int b = 0; b < NRC_TRAIN_BATCH_COUNT; ++b)
 		p.train_records[b] = d_train_records ? d_train_records[b] : nullptr;
 	return h->state.Infer(p, nullptr, h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
+}
+
+// ---- the reference's record formats (NRCEvalRecord / NRCTrainRecord) + scene gather
+static int check_scene(const NrcScene *sc) {
+	NRC_REQUIRE(sc, "null scene");
+	NRC_REQUIRE(sc->vertices && sc->vertex_indices && sc->texcoords && sc->texcoord_indices && sc->materials && sc->material_ids && sc->transforms,
+	            "scene: a buffer pointer is null");
+	NRC_REQUIRE(sc->texture_count == 0 || sc->textures, "scene: texture table is null");
+	NRC_REQUIRE(((uintptr_t)sc->transforms & 15u) == 0 && ((uintptr_t)sc->materials & 15u) == 0 && ((uintptr_t)sc->texcoords & 7u) == 0,
+	            "scene: transforms / materials must be 16-byte aligned, texcoords 8-byte aligned");
+	return NRC_OK;
+}
+
+int nrc_infer(nrc_handle_t h, const void *d_eval_records, const uint32_t *d_count, uint64_t max_count, const NrcScene *scene,
+              void *d_bias_factor_r, const void *d_factor_gb, uint32_t image_pitch, void *const d_train_records[4], void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	if (max_count == 0)
+		return NRC_OK;
+	NRC_REQUIRE(d_eval_records && ((uintptr_t)d_eval_records & 3u) == 0, "nrc_infer: eval records must be 4-byte aligned");
+	int rc = check_scene(scene);
+	if (rc != NRC_OK)
+		return rc;
+	InferParams p{};
+	p.n = max_count, p.d_count = d_count, p.in_mode = NRC_IN_PACKED, p.out_mode = NRC_OUT_SCATTER, p.clamp_output = 1;
+	p.in = (const uint8_t *)d_eval_records + offsetof(NrcEvalRecord, packed_input), p.in_stride_bytes = sizeof(NrcEvalRecord), p.scene = *scene;
+	p.dst = (const uint32_t *)d_eval_records, p.dst_stride_u32 = sizeof(NrcEvalRecord) / 4;
+	p.bias_factor_r = d_bias_factor_r, p.factor_gb = d_factor_gb, p.image_pitch = image_pitch;
+	for (int b = 0; b < NRC_TRAIN_BATCH_COUNT; ++b)
+		p.train_records[b] = d_train_records ? d_train_records[b] : nullptr;
+	return h->state.Infer(p, nullptr, h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
+}
+
+int nrc_infer_packed(nrc_handle_t h, const void *d_packed_inputs, uint32_t stride_bytes, const uint32_t *d_count, uint64_t max_count,
+                     const NrcScene *scene, void *d_out, void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	if (max_count == 0)
+		return NRC_OK;
+	NRC_REQUIRE(d_packed_inputs && d_out, "nrc_infer_packed: null buffer");
+	NRC_REQUIRE(stride_bytes >= 16 && stride_bytes % 4 == 0 && ((uintptr_t)d_packed_inputs & 3u) == 0,
+	            "nrc_infer_packed: inputs must be 4-byte aligned, stride >= 16 and a multiple of 4");
+	int rc = check_scene(scene);
+	if (rc != NRC_OK)
+		return rc;
+	InferParams p{};
+	p.n = max_count, p.d_count = d_count, p.in_mode = NRC_IN_PACKED, p.out_mode = NRC_OUT_F16VEC3, p.clamp_output = 1;
+	p.in = d_packed_inputs, p.in_stride_bytes = stride_bytes, p.scene = *scene, p.out = d_out;
+	return h->state.Infer(p, nullptr, h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
+}
+
+int nrc_unpack_inputs(const void *d_packed_inputs, uint32_t stride_bytes, uint64_t n, const NrcScene *scene, float *d_unpacked14, void *stream) {
+	if (n == 0)
+		return NRC_OK;
+	NRC_REQUIRE(d_packed_inputs && d_unpacked14, "nrc_unpack_inputs: null buffer");
+	NRC_REQUIRE(stride_bytes >= 16 && stride_bytes % 4 == 0 && ((uintptr_t)d_packed_inputs & 3u) == 0 && ((uintptr_t)d_unpacked14 & 7u) == 0,
+	            "nrc_unpack_inputs: inputs 4-byte aligned with stride >= 16 (multiple of 4), outputs 8-byte aligned");
+	int rc = check_scene(scene);
+	if (rc != NRC_OK)
+		return rc;
+	std::string err;
+	int sms = 0;
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess || (rc = check_device(dev, &sms, &err)) != NRC_OK)
+		return set_error(rc != NRC_OK ? rc : NRC_ERR_CUDA, err.empty() ? "cudaGetDevice failed" : err);
+	cudaError_t e = launch_unpack(d_packed_inputs, stride_bytes, n, *scene, d_unpacked14, (cudaStream_t)stream);
+	if (e != cudaSuccess)
+		return set_error(NRC_ERR_CUDA, std::string("nrc_unpack_kernel: ") + cudaGetErrorString(e));
+	return NRC_OK;
+}
+
+static void fill_record_batch(nrc_handle_t h, GradParams &p, const void *d_records, uint32_t *d_count, uint32_t max_count, const NrcScene *scene) {
+	p.n = max_count, p.d_count = d_count, p.in_mode = NRC_IN_PACKED, p.loss_kind = NRC_LOSS_RELATIVE_L2_LUMINANCE, p.loss_scale = NRC_LOSS_SCALE;
+	p.in = (const uint8_t *)d_records + offsetof(NrcTrainRecord, packed_input), p.in_stride_bytes = sizeof(NrcTrainRecord), p.scene = *scene;
+	p.target = d_records, p.target_stride_bytes = sizeof(NrcTrainRecord), p.target_is_f16 = 0; // target = bias (nrc_gradient.comp:31-33)
+	p.y_out = h->state.GetPredictionCapture();
+}
+static int train_records_impl(nrc_handle_t h, const void *d_records, uint32_t *d_count, uint32_t max_count, const NrcScene *scene, void *stream,
+                              int adam_mode) {
+	NRC_REQUIRE(h, "null handle");
+	NRC_REQUIRE(max_count == 0 || (d_records && ((uintptr_t)d_records & 3u) == 0), "training: train records must be 4-byte aligned");
+	int rc = check_scene(scene);
+	if (rc != NRC_OK)
+		return rc;
+	TrainParams tp{};
+	fill_record_batch(h, tp.batch[0], d_records, d_count, max_count, scene);
+	tp.num_batches = 1, tp.adam_mode[0] = adam_mode, tp.gradients = h->state.GetGradientBuffer(), tp.limit = NRC_GRAD_STRIDE, tp.batch_cap = max_count;
+	return h->state.Train(tp, nullptr, h->state.GetWeightBuffer(), (cudaStream_t)stream);
+}
+int nrc_gradient(nrc_handle_t h, const void *d_records, uint32_t *d_count, uint32_t max_count, const NrcScene *scene, void *stream) {
+	return train_records_impl(h, d_records, d_count, max_count, scene, stream, 0);
+}
+int nrc_train_batch(nrc_handle_t h, const void *d_records, uint32_t *d_count, uint32_t max_count, const NrcScene *scene, int write_use_weights,
+                    void *stream) {
+	return train_records_impl(h, d_records, d_count, max_count, scene, stream, write_use_weights ? 2 : 1);
+}
+int nrc_train_frame(nrc_handle_t h, void *const d_records[4], uint32_t *const d_counts[4], uint32_t max_count, const NrcScene *scene, void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	NRC_REQUIRE(d_records, "nrc_train_frame: null buffer table");
+	int rc = check_scene(scene);
+	if (rc != NRC_OK)
+		return rc;
+	TrainParams tp{};
+	for (int b = 0; b < NRC_TRAIN_BATCH_COUNT; ++b) {
+		NRC_REQUIRE(max_count == 0 || (d_records[b] && ((uintptr_t)d_records[b] & 3u) == 0), "nrc_train_frame: train records must be 4-byte aligned");
+		fill_record_batch(h, tp.batch[b], d_records[b], d_counts ? d_counts[b] : nullptr, max_count, scene);
+		if (b != NRC_TRAIN_BATCH_COUNT - 1)
+			tp.batch[b].y_out = nullptr; // the capture buffer holds one batch: keep the last batch's predictions
+		tp.adam_mode[b] = b == NRC_TRAIN_BATCH_COUNT - 1 ? 2 : 1; // use_weights by the last batch only (NRCRenderGraph.cpp:66-68)
+	}
+	tp.num_batches = NRC_TRAIN_BATCH_COUNT, tp.gradients = h->state.GetGradientBuffer(), tp.limit = NRC_GRAD_STRIDE, tp.batch_cap = max_count;
+	return h->state.Train(tp, nullptr, h->state.GetWeightBuffer(), (cudaStream_t)stream);
 }
 
 static int check_unpacked_args(const char *who, const void *d_inputs, uint32_t input_stride, const void *d_targets, uint32_t target_stride,

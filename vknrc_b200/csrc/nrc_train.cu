@@ -25,6 +25,7 @@
 // and (optionally) nrc_optimize.comp is applied verbatim to that slice -> grid barrier -> next batch of the frame.
 #include "nrc_kernels.h"
 #include "nrc_encode.cuh"
+#include "nrc_unpack.cuh"
 
 using namespace sm100;
 
@@ -369,7 +370,15 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 #pragma unroll
 					for (int i = 0; i < 16; ++i)
 						o[i] = 0u; // nrc_gradient.comp:27-34: zero input + zero target => exactly zero contribution
-					if (IN_MODE == NRC_IN_UNPACKED) {
+					if (IN_MODE == NRC_IN_PACKED) { // nrc_gradient.comp:29-31: UnpackNRCInput, then the same encoding
+						if (valid) {
+							float in[14];
+							uint32_t pk[4];
+							load_packed_input(p.in, gi, p.in_stride_bytes, pk);
+							unpack_nrc_input(p.scene, pk, in);
+							encode_nrc_half(in, h, o);
+						}
+					} else if (IN_MODE == NRC_IN_UNPACKED) {
 						if (valid) {
 							float in[14];
 							const float2 *src = (const float2 *)((const uint8_t *)p.in + gi * p.in_stride_bytes);
@@ -705,6 +714,8 @@ cudaError_t launch_train(const TrainParams &p, const CUtensorMap &tm_w, const CU
 		return launch_train_t<NRC_IN_UNPACKED>(p, tm_w, tm_in, grid, stream);
 	case NRC_IN_IMAGE_RANDOM:
 		return launch_train_t<NRC_IN_IMAGE_RANDOM>(p, tm_w, tm_in, grid, stream);
+	case NRC_IN_PACKED:
+		return launch_train_t<NRC_IN_PACKED>(p, tm_w, tm_in, grid, stream);
 	}
 	return cudaErrorInvalidValue;
 }
