@@ -221,6 +221,31 @@ def main():
             ms_u = timed(lambda: st.infer_unpacked(rec, outputs=out), max(10, K // 4), 3)
             extra["infer_unpacked_queries_per_s"] = world * n / (ms_u * 1e-3)
             extra["infer_unpacked_ms_per_step"] = ms_u
+            # the reference's own formats: 20-byte NRCEvalRecord per pixel + scene gather (UnpackNRCInput) -> composite into the
+            # rgba32f / rg32f screen images: the exact nrc_inference.comp pass (nrc_infer), from device and from host records
+            from vknrc_b200 import synth
+            sa = synth.make_scene_arrays(7, n_prims=20000, n_instances=8, n_materials=64, n_textures=8)
+            scene = nrc.DeviceScene(sa["vertices"], sa["vertex_indices"], sa["texcoords"], sa["texcoord_indices"], sa["materials"],
+                                    sa["material_ids"], sa["transforms"], sa["textures"], device=local)
+            ev = synth.eval_records_screen(11 + rank, 1920, 1080, 20000, 8)
+            h_ev = torch.from_numpy(ev.view(np.uint8).reshape(-1)).pin_memory()
+            d_ev = h_ev.to(dev)
+            d_bf = torch.rand((1080, 1920, 4), device=dev, generator=g)
+            d_gb = torch.rand((1080, 1920, 2), device=dev, generator=g)
+            d_trs = [torch.zeros(nrc.TRAIN_BATCH_SIZE * 40, dtype=torch.uint8, device=dev) for _ in range(4)]
+            cnt = torch.tensor([n], dtype=torch.int32, device=dev)
+            ms_r = timed(lambda: st.infer(d_ev, cnt, scene, d_bf, d_gb, 1920, d_trs, max_count=n), max(10, K // 4), 3)
+            extra["infer_eval_records_scatter_queries_per_s"] = world * n / (ms_r * 1e-3)
+            extra["infer_eval_records_scatter_ms_per_step"] = ms_r
+            h_bf = torch.empty((1080, 1920, 4), dtype=torch.float32).pin_memory()
+
+            def e2e_records():  # host records in, composited image back: 41.5 MB up, 33.2 MB down per frame
+                d_ev.copy_(h_ev, non_blocking=True)
+                st.infer(d_ev, cnt, scene, d_bf, d_gb, 1920, d_trs, max_count=n)
+                h_bf.copy_(d_bf, non_blocking=True)
+            ms_re = timed(e2e_records, max(3, min(K, 20)), 3)
+            extra["e2e_eval_records_queries_per_s"] = world * n / (ms_re * 1e-3)
+            extra["e2e_eval_records_ms_per_step"] = ms_re
             # training: one frame = 4 dependent batches of 16384 records (configs[3]); records sharded per GPU
             nb = nrc.TRAIN_BATCH_SIZE
             trec = torch.rand((4, nb, 14), device=dev, generator=g)
@@ -234,6 +259,10 @@ def main():
                 # the whole frame (4 x [gradient -> reduce -> (NVLink all-reduce) -> Adam]) is ONE cooperative kernel launch
                 st.train_frame_unpacked(trecs, ttgts)
             ms_t = timed(train_frame, max(10, K // 4), 3)
+            # the same frame on 40-byte NRCTrainRecord buffers (scene gather fused), the reference's NNTrain input
+            d_trec = [torch.from_numpy(synth.train_records(100 + 10 * rank + b, nb, 20000, 8).view(np.uint8).reshape(-1)).to(dev) for b in range(4)]
+            ms_tr = timed(lambda: st.train_frame(d_trec, scene, max_count=nb), max(10, K // 4), 3)
+            extra["train_records_frame_ms_4x16384"] = ms_tr
             extra["train_records_per_s"] = world * 4 * nb / (ms_t * 1e-3)
             extra["train_ms_per_frame_4x16384"] = ms_t
             extra["train_tflops"] = world * 4 * nb * FLOP_PER_TRAIN_RECORD / (ms_t * 1e-3) / 1e12

@@ -455,9 +455,9 @@ typedef struct { const float *vertices; const uint32_t *vertex_indices; const fl
                  const NrcOracleMaterial *materials; const uint32_t *material_ids; const float *transforms;
                  const NrcOracleTexture *textures; uint32_t texture_count; } NrcOracleScene;
 
-static float srgb_to_linear(uint8_t c) {
-	float x = (float)c / 255.0f;
-	return x <= 0.04045f ? x / 12.92f : powf((x + 0.055f) / 1.055f, 2.4f);
+static float srgb_to_linear(uint8_t c) { /* the sRGB EOTF, evaluated in double and rounded once to fp32 */
+	double x = (double)c / 255.0;
+	return (float)(x <= 0.04045 ? x / 12.92 : pow((x + 0.055) / 1.055, 2.4));
 }
 static void sample_texture(const NrcOracleTexture *t, float u, float v, float rgb[3]) {
 	float x = u * (float)t->width - 0.5f, y = v * (float)t->height - 0.5f;

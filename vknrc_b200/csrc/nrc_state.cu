@@ -306,6 +306,30 @@ static int bad_arg(const char *what) { return set_error(NRC_ERR_INVALID_ARGUMENT
 			return bad_arg(msg);                                                                                       \
 	} while (0)
 
+// ---- handle-less test-harness kernels: a lazily created per-device scratch state supplies the partial buffers
+static NrcState *scratch_state(int *rc) {
+	static std::mutex mu;
+	static std::vector<NrcState *> per_device;
+	int dev = 0;
+	if (cudaGetDevice(&dev) != cudaSuccess) {
+		*rc = set_error(NRC_ERR_CUDA, "cudaGetDevice failed");
+		return nullptr;
+	}
+	std::lock_guard<std::mutex> lock(mu);
+	if ((int)per_device.size() <= dev)
+		per_device.resize(dev + 1, nullptr);
+	if (!per_device[dev]) {
+		NrcState *s = new (std::nothrow) NrcState(dev, Extent2D{0, 0}, 0);
+		if (!s || !s->ok()) {
+			*rc = set_error(s ? s->error_code() : NRC_ERR_OUT_OF_MEMORY, s ? s->error() : "host allocation failed");
+			delete s;
+			return nullptr;
+		}
+		per_device[dev] = s;
+	}
+	return per_device[dev];
+}
+
 extern "C" {
 
 const char *nrc_last_error(void) { return g_last_error.c_str(); }
@@ -384,30 +408,6 @@ int nrc_comm_shutdown(nrc_handle_t h) {
 	return h->state.CommShutdown();
 }
 uint32_t nrc_comm_world(nrc_handle_t h) { return h ? h->state.comm_world() : 0u; }
-
-// ---- handle-less test-harness kernels: a lazily created per-device scratch state supplies the partial buffers
-static NrcState *scratch_state(int *rc) {
-	static std::mutex mu;
-	static std::vector<NrcState *> per_device;
-	int dev = 0;
-	if (cudaGetDevice(&dev) != cudaSuccess) {
-		*rc = set_error(NRC_ERR_CUDA, "cudaGetDevice failed");
-		return nullptr;
-	}
-	std::lock_guard<std::mutex> lock(mu);
-	if ((int)per_device.size() <= dev)
-		per_device.resize(dev + 1, nullptr);
-	if (!per_device[dev]) {
-		NrcState *s = new (std::nothrow) NrcState(dev, Extent2D{0, 0}, 0);
-		if (!s || !s->ok()) {
-			*rc = set_error(s ? s->error_code() : NRC_ERR_OUT_OF_MEMORY, s ? s->error() : "host allocation failed");
-			delete s;
-			return nullptr;
-		}
-		per_device[dev] = s;
-	}
-	return per_device[dev];
-}
 
 int nrc_mlp_evaluate_encoded(const void *d_weights, const void *d_inputs, void *d_outputs, uint64_t n, void *stream) {
 	if (n == 0)
@@ -536,11 +536,9 @@ int nrc_unpack_inputs(const void *d_packed_inputs, uint32_t stride_bytes, uint64
 	int rc = check_scene(scene);
 	if (rc != NRC_OK)
 		return rc;
-	std::string err;
-	int sms = 0;
-	int dev = 0;
-	if (cudaGetDevice(&dev) != cudaSuccess || (rc = check_device(dev, &sms, &err)) != NRC_OK)
-		return set_error(rc != NRC_OK ? rc : NRC_ERR_CUDA, err.empty() ? "cudaGetDevice failed" : err);
+	NrcState *s = scratch_state(&rc); // (also the "is this an sm_100 device" check, done once per device)
+	if (!s)
+		return rc;
 	cudaError_t e = launch_unpack(d_packed_inputs, stride_bytes, n, *scene, d_unpacked14, (cudaStream_t)stream);
 	if (e != cudaSuccess)
 		return set_error(NRC_ERR_CUDA, std::string("nrc_unpack_kernel: ") + cudaGetErrorString(e));

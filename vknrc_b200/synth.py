@@ -1,0 +1,74 @@
+"""Synthetic inputs in the reference's buffer layouts, for tests and bench.py (numpy only, no CUDA): a random scene
+(shader/src/Scene.glsl:8-71 layouts) and PackedNRCInput / NRCEvalRecord / NRCTrainRecord arrays (shader/src/NRCRecord.glsl:6-38)
+with the statistics SURVEY 8d lists for configs 3 and 4. There is no network access for real scenes; the path tracer that
+produces real records is out of scope."""
+from __future__ import annotations
+
+import numpy as np
+
+from .api import EVAL_RECORD_DTYPE, MATERIAL_DTYPE, TRAIN_RECORD_DTYPE
+
+
+def make_scene_arrays(seed: int, n_prims: int = 500, n_instances: int = 3, n_materials: int = 12, n_textures: int = 3) -> dict:
+    """Non-degenerate triangles inside about [-2, 2]^3, rigid instance transforms, materials of which about half sample a
+    diffuse and / or specular sRGB texture (texture coordinates also outside [0,1]: REPEAT addressing)."""
+    rng = np.random.default_rng(seed)
+    n_verts = 3 * n_prims
+    centres = rng.uniform(-1.5, 1.5, (n_prims, 1, 3))
+    # well-conditioned triangles (no slivers: a sliver's fp32 normal is ill-defined in the reference as well)
+    frame = np.linalg.qr(rng.standard_normal((n_prims, 3, 3)))[0]
+    ang = 2 * np.pi * np.arange(3)[None, :] / 3 + rng.uniform(-0.5, 0.5, (n_prims, 3))
+    rad = rng.uniform(0.2, 0.5, (n_prims, 3))
+    offs = (rad * np.cos(ang))[..., None] * frame[:, None, :, 0] + (rad * np.sin(ang))[..., None] * frame[:, None, :, 1]
+    vertices = (centres + offs).reshape(n_verts, 3).astype(np.float32)
+    vertex_indices = np.arange(n_verts, dtype=np.uint32).reshape(n_prims, 3)
+    texcoords = rng.uniform(-1.0, 2.0, (n_verts, 2)).astype(np.float32)
+    texcoord_indices = rng.permutation(n_verts).astype(np.uint32).reshape(n_prims, 3)
+    mats = np.zeros(n_materials, MATERIAL_DTYPE)
+    mats["diffuse"], mats["specular"], mats["emission"] = rng.uniform(0, 1, (3, n_materials, 3))
+    mats["roughness"], mats["metallic"], mats["ior"] = rng.uniform(0, 1, n_materials), rng.uniform(0, 1, n_materials), 1.5
+    for key in ("diffuse_texture_id", "specular_texture_id", "emission_texture_id"):
+        ids = rng.integers(0, max(1, n_textures), n_materials).astype(np.uint32)
+        ids[rng.uniform(size=n_materials) < 0.5] = 0xFFFFFFFF
+        mats[key] = ids if n_textures else 0xFFFFFFFF
+    material_ids = rng.integers(0, n_materials, n_prims).astype(np.uint32)
+    transforms = np.zeros((n_instances, 12), np.float32)
+    for i in range(n_instances):
+        q, _ = np.linalg.qr(rng.standard_normal((3, 3)))
+        t = rng.uniform(-1, 1, 3)
+        for j in range(3):  # column j of the mat3x4 = {row j of the rotation, translation j}
+            transforms[i, 4 * j:4 * j + 3], transforms[i, 4 * j + 3] = q[j], t[j]
+    textures = [rng.integers(0, 256, (int(rng.integers(3, 40)), int(rng.integers(3, 40)), 4), dtype=np.uint8) for _ in range(n_textures)]
+    return {"vertices": vertices, "vertex_indices": vertex_indices, "texcoords": texcoords, "texcoord_indices": texcoord_indices,
+            "materials": mats, "material_ids": material_ids, "transforms": transforms, "textures": textures}
+
+
+def random_packed_inputs(seed: int, n: int, n_prims: int, n_instances: int) -> np.ndarray:
+    """[n,4] uint32 PackedNRCInput (NRCRecord.glsl:6-10): primitive, flip bit | instance, barycentric y,z, scattered dir."""
+    rng = np.random.default_rng(seed)
+    prim = rng.integers(0, n_prims, n).astype(np.uint32)
+    inst = rng.integers(0, n_instances, n).astype(np.uint32) | (rng.integers(0, 2, n).astype(np.uint32) << 31)
+    b = rng.dirichlet((1, 1, 1), n)
+    bary = (np.round(b[:, 1] * 65535).astype(np.uint32) & 0xFFFF) | (np.round(b[:, 2] * 65535).astype(np.uint32) << 16)
+    sd = rng.integers(0, 65536, (n, 2)).astype(np.uint32)
+    return np.stack([prim, inst, bary, sd[:, 0] | (sd[:, 1] << 16)], axis=1).astype(np.uint32)
+
+
+def eval_records_screen(seed: int, width: int, height: int, n_prims: int, n_instances: int) -> np.ndarray:
+    """One NRCEvalRecord per pixel, dst = screen (x, y) (NRCRecord.glsl:19): the inference workload of a frame whose every
+    primary path ends in a cache query."""
+    n = width * height
+    ev = np.zeros(n, EVAL_RECORD_DTYPE)
+    idx = np.arange(n, dtype=np.uint32)
+    ev["dst"] = ((idx % width) | ((idx // width) << 15)) << 1
+    ev["packed_input"] = np.ascontiguousarray(random_packed_inputs(seed, n, n_prims, n_instances)).view(EVAL_RECORD_DTYPE["packed_input"]).reshape(n)
+    return ev
+
+
+def train_records(seed: int, n: int, n_prims: int, n_instances: int) -> np.ndarray:
+    """[n] NRCTrainRecord: bias (= target radiance) and factor U(0,1)^3 + a PackedNRCInput."""
+    rng = np.random.default_rng(seed)
+    r = np.zeros(n, TRAIN_RECORD_DTYPE)
+    r["bias"], r["factor"] = rng.uniform(0, 1, (n, 3)), rng.uniform(0, 1, (n, 3))
+    r["packed_input"] = np.ascontiguousarray(random_packed_inputs(seed + 1, n, n_prims, n_instances)).view(TRAIN_RECORD_DTYPE["packed_input"]).reshape(n)
+    return r
