@@ -21,8 +21,8 @@ int main(int argc, char **argv) {
 	CUtensorMap tw; mk(&tw, w, 323, 64);
 	const int nb = argc > 2 ? atoi(argv[2]) : 1; // batches per launch (frame = 4)
 	NrcOptimizerEntry *entries; NrcOptimizerState *ost; uint32_t *sync; float *grads; __half *uw;
-	cudaMalloc(&entries, 20672 * 16); cudaMalloc(&ost, 20); cudaMalloc(&sync, 16); cudaMalloc(&grads, NRC_GRAD_STRIDE * 4); cudaMalloc(&uw, 6 * 8192);
-	cudaMemset(entries, 0, 20672 * 16); cudaMemset(sync, 0, 16);
+	cudaMalloc(&entries, 20672 * 16); cudaMalloc(&ost, 20); cudaMalloc(&sync, 32); cudaMalloc(&grads, NRC_GRAD_STRIDE * 4); cudaMalloc(&uw, 6 * 8192);
+	cudaMemset(entries, 0, 20672 * 16); cudaMemset(sync, 0, 32);
 	const NrcOptimizerState st0{0u, 1.0f, 1.0f, 1.0f, 0.0f}; cudaMemcpy(ost, &st0, 20, cudaMemcpyHostToDevice);
 	nrc::TrainParams tp{};
 	for (int b = 0; b < nb; ++b) {

@@ -103,7 +103,7 @@ struct TrainParams {
 	uint32_t limit;        // number of leading elements to produce (20672 for a caller's dW, NRC_GRAD_STRIDE otherwise)
 	uint32_t batch_cap;    // d_count is clamped in place to this (nrc_train_prepare.comp:17-19)
 	AdamParams adam;       // use_weights / use_ema are taken from here when adam_mode == 2
-	uint32_t *grid_bar;    // {arrival count, generation}: zero-initialised, owned by the state object
+	uint32_t *grid_bar;    // {arrival count (even gen), arrival count (odd gen), generation}: zero-initialised, owned by the state
 	CommParams comm;
 };
 

@@ -119,7 +119,7 @@ NrcState::NrcState(int device, Extent2D extent, uint64_t seed) : m_device(device
 	    !alloc((void **)&m_optimizer_entries, sizeof(NrcOptimizerEntry) * NRC_WEIGHT_COUNT) ||
 	    !alloc((void **)&m_gradients, sizeof(float) * NRC_GRAD_STRIDE) ||
 	    !alloc((void **)&m_partials, sizeof(float) * NRC_GRAD_STRIDE * gradient_max_partials(m_sms)) ||
-	    !alloc((void **)&m_sync_words, 4 * sizeof(uint32_t)))
+	    !alloc((void **)&m_sync_words, 8 * sizeof(uint32_t)))
 		return;
 	m_ok = true;
 	if (ResetMLPBuffers(seed) != NRC_OK)
@@ -202,7 +202,7 @@ int NrcState::upload_initial(const float *w) {
 	NRC_CUDA_TRY(cudaMemcpy(m_use_weights, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice), sink);
 	NRC_CUDA_TRY(cudaMemcpy(m_optimizer_entries, e.data(), e.size() * sizeof(NrcOptimizerEntry), cudaMemcpyHostToDevice), sink);
 	NRC_CUDA_TRY(cudaMemcpy(m_optimizer_state, &st, sizeof(st), cudaMemcpyHostToDevice), sink);
-	NRC_CUDA_TRY(cudaMemset(m_sync_words, 0, 4 * sizeof(uint32_t)), sink);
+	NRC_CUDA_TRY(cudaMemset(m_sync_words, 0, 8 * sizeof(uint32_t)), sink);
 	return NRC_OK;
 }
 

@@ -98,7 +98,7 @@ private:
 	NrcOptimizerState *m_optimizer_state{nullptr};
 	NrcOptimizerEntry *m_optimizer_entries{nullptr};
 	float *m_gradients{nullptr}, *m_partials{nullptr};
-	uint32_t *m_sync_words{nullptr}; // [0] optimizer "last CTA" counter, [2..3] grid barrier {count, generation}
+	uint32_t *m_sync_words{nullptr}; // [0] optimizer "last CTA" counter, [2..4] grid barrier {count even, count odd, generation}
 	float *m_prediction_capture{nullptr};
 
 	uint64_t *m_comm_local{nullptr};

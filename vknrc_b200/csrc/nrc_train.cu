@@ -121,22 +121,31 @@ __device__ __forceinline__ void publish_state_if_last(const AdamParams &a, const
 // Grid barrier. All CTAs of the (cooperative) launch are co-resident. bar[0] = arrival count, bar[1] = generation.
 // Writers' global stores become visible to every later reader, including TMA (async proxy) reads of updated weights.
 // ------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void grid_sync(uint32_t *bar) {
-	asm volatile("fence.proxy.async;" ::: "memory");
+// ------------------------------------------------------------------------------------------------------------------
+// Grid barrier. All CTAs of the (cooperative) launch are co-resident. bar[0], bar[1] = arrival counters used by even /
+// odd generations, bar[2] = generation. Release: the CTA barrier orders every thread's global writes before thread 0's
+// __threadfence + arrival. Acquire: readers after the barrier use L2 loads (ld.cg / TMA / volatile), so no trailing fence.
+// The last arriver resets its counter with a plain store: that counter is next used two generations later, i.e. after
+// this CTA's own next arrival fence. kProxyFence: the writes before the barrier (the new weights) are read through the
+// async proxy (TMA) after it.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool kProxyFence> __device__ __forceinline__ void grid_sync(uint32_t *bar) {
+	if (kProxyFence)
+		asm volatile("fence.proxy.async;" ::: "memory");
 	__syncthreads();
 	if (threadIdx.x == 0) {
-		volatile uint32_t *gen = bar + 1;
-		const uint32_t my_gen = *gen; // cannot advance before this CTA has arrived
+		uint32_t my_gen, seen;
+		asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(my_gen) : "l"(bar + 2) : "memory"); // cannot advance before this CTA arrives
 		__threadfence();
-		if (atomicAdd(bar, 1u) == gridDim.x - 1) {
-			bar[0] = 0;
-			__threadfence();
-			atomicAdd(bar + 1, 1u);
+		uint32_t *count = bar + (my_gen & 1u);
+		if (atomicAdd(count, 1u) == gridDim.x - 1) {
+			*count = 0;
+			asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar + 2), "r"(my_gen + 1) : "memory");
 		} else {
-			while (*gen == my_gen)
-				__nanosleep(32);
+			do {
+				asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar + 2) : "memory");
+			} while (seen == my_gen);
 		}
-		__threadfence();
 	}
 	__syncthreads();
 }
@@ -177,8 +186,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	uint8_t *w_sm = smem + kWOff, *act_sm = smem + kActOff, *delta_sm = smem + kDeltaOff;
 	uint64_t *bars = (uint64_t *)(smem + kBarOff);
-	uint64_t *w_full = bars, *in_full = bars + 1, *d_full = bars + 2, *tile_done = bars + 3, *a_ready = bars + 4;
-	uint32_t *tmem_slot = (uint32_t *)(bars + 5);
+	uint64_t *w_full = bars, *in_full = bars + 1, *d_full = bars + 2, *tile_done = bars + 3, *a_ready = bars + 4, *w_ready = bars + 5;
+	uint32_t *tmem_slot = (uint32_t *)(bars + 6);
 #ifdef NRC_TRACE
 	__shared__ uint2 gtrace[NRC_GTRACE_CAP];
 	uint32_t gtrace_n = 0;
@@ -191,6 +200,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 
 	if (threadIdx.x == 0) {
 		mbar_init(w_full, 1), mbar_init(in_full, 1), mbar_init(d_full, 1), mbar_init(tile_done, 1), mbar_init(a_ready, kEpiWarps);
+		mbar_init(w_ready, kEpiWarps);
 		fence_mbar_init();
 	}
 	if (warp == kIssueWarp)
@@ -228,23 +238,106 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			*(uint4 *)(r + (((4 * h + c) ^ (row & 7)) << 4)) = make_uint4(o16[4 * c], o16[4 * c + 1], o16[4 * c + 2], o16[4 * c + 3]);
 	};
 
+	// this thread's half row of a_0 for record `tile * 128 + row` of batch `bp` (n = the batch's clamped record count)
+	auto encode_tile_row = [&](const GradParams &bp, uint64_t n, uint32_t tile) {
+		const uint64_t gi = (uint64_t)tile * NRC_TILE + row;
+		const bool valid = gi < n;
+		uint32_t o[16];
+#pragma unroll
+		for (int i = 0; i < 16; ++i)
+			o[i] = 0u; // nrc_gradient.comp:27-34: zero input + zero target => exactly zero contribution
+		if (IN_MODE == NRC_IN_PACKED) { // nrc_gradient.comp:29-31: UnpackNRCInput, then the same encoding
+			if (valid) {
+				float in[14];
+				uint32_t pk[4];
+				load_packed_input(bp.in, gi, bp.in_stride_bytes, pk);
+				unpack_nrc_input(bp.scene, pk, in);
+				encode_nrc_half(in, h, o);
+			}
+		} else if (IN_MODE == NRC_IN_UNPACKED) {
+			if (valid) {
+				float in[14];
+				const float2 *src = (const float2 *)((const uint8_t *)bp.in + gi * bp.in_stride_bytes);
+#pragma unroll
+				for (int i = 0; i < 7; ++i) {
+					const float2 t = __ldg(src + i);
+					in[2 * i] = t.x, in[2 * i + 1] = t.y;
+				}
+				encode_nrc_half(in, h, o);
+			}
+		} else if (IN_MODE == NRC_IN_IMAGE_RANDOM) { // gradient.comp:47-49
+			uint32_t px = bp.seed_x + (uint32_t)(gi % 128u), py = bp.seed_y + (uint32_t)(gi / 128u);
+			pcg2d(px, py);
+			const float sc = 1.0f / (float)0xffffffffu;
+			if (valid)
+				encode_oneblob32_half(sc * (float)(h ? py : px), o);
+		}
+		store_half_row(act_sm, o);
+	};
+	auto batch_count = [&](const GradParams &bp) -> uint64_t { // nrc_train_prepare.comp:17-18: count = min(count, capacity)
+		uint64_t n = bp.n;
+		if (bp.d_count) {
+			const uint64_t c = *(volatile uint32_t *)bp.d_count;
+			n = c < n ? c : n;
+		}
+		return n;
+	};
+	auto tiles_of_this_cta = [&](uint64_t n) -> uint32_t {
+		const uint32_t ntiles = (uint32_t)((n + NRC_TILE - 1) / NRC_TILE);
+		return blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+	};
+
 	// phases / counters that run across tiles and batches
 	uint32_t d_ph = 0;      // epilogue threads: parity of the next d_full completion
 	uint32_t ar_ph = 0;     // issuer: parity of the next a_ready completion
 	uint32_t tile_base = 0; // tiles this CTA processed in earlier batches (tile_done / in_full phase = tile number & 1)
-	uint32_t w_loads = 0;   // weight loads so far (w_full phase)
+
+	// The first tile of a batch is encoded ahead of time: for batch 0 right here (while the weights stream in), for batch
+	// b + 1 at the end of batch b's gradient phase - before the grid barriers, the reduction and the weight reload, none of
+	// which the encoding depends on.
+	uint64_t n = batch_count(tp.batch[0]);
+	uint32_t my_tiles = tiles_of_this_cta(n);
+	if (IN_MODE != NRC_IN_ENCODED && warp < kEpiWarps && my_tiles) {
+		encode_tile_row(tp.batch[0], n, blockIdx.x);
+		arrive_a_ready();
+	}
+	uint32_t w_reloads = 0; // weight re-stagings by the epilogue warps so far (w_ready phase)
 
 #pragma unroll 1
 	for (uint32_t b = 0; b < tp.num_batches; ++b) {
 		const GradParams &p = tp.batch[b];
-		uint64_t n = p.n;
-		if (p.d_count) { // nrc_train_prepare.comp:17-18: count = min(count, NRC_TRAIN_BATCH_SIZE)
-			const uint64_t c = *p.d_count;
-			n = c < n ? c : n;
-		}
-		const uint32_t ntiles = (uint32_t)((n + NRC_TILE - 1) / NRC_TILE);
-		const uint32_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 		float *my_partial = p.partials + (size_t)blockIdx.x * NRC_GRAD_STRIDE;
+		// the next batch's record count is read now (nothing writes it before that batch's own reduction phase)
+		uint64_t n_next = 0;
+		uint32_t tiles_next = 0;
+		if (b + 1 < tp.num_batches) {
+			n_next = batch_count(tp.batch[b + 1]);
+			tiles_next = tiles_of_this_cta(n_next);
+		}
+		if (b > 0 && my_tiles && warp < kEpiWarps) {
+			// Re-stage the weights the previous batch's optimizer phase just wrote (by other SMs; the grid barrier made them
+			// visible in L2): plain 16-byte L2 loads into the swizzled tile, no global cross-proxy fence needed. Rows past 323
+			// keep the zeros TMA filled in for batch 0.
+			const uint4 *src = (const uint4 *)tp.adam.weights;
+			constexpr int kPerThread = (NRC_WEIGHT_ROWS * 8 + kEpiThreads - 1) / kEpiThreads; // 11: every load in flight at once
+			uint4 v[kPerThread];
+#pragma unroll
+			for (int u = 0; u < kPerThread; ++u) {
+				const uint32_t idx = threadIdx.x + u * kEpiThreads;
+				if (idx < NRC_WEIGHT_ROWS * 8)
+					asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + idx));
+			}
+#pragma unroll
+			for (int u = 0; u < kPerThread; ++u) {
+				const uint32_t idx = threadIdx.x + u * kEpiThreads, r = idx >> 3, c = idx & 7u;
+				if (idx < NRC_WEIGHT_ROWS * 8)
+					*(uint4 *)(w_sm + r * 128 + ((c ^ (r & 7u)) << 4)) = v[u];
+			}
+			fence_proxy_async_smem();
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(w_ready);
+		}
 
 		if (my_tiles == 0) { // nothing to do: contribute an all-zero partial so the reduction stays shape-stable
 			for (uint32_t i = threadIdx.x; i < NRC_GRAD_STRIDE; i += blockDim.x)
@@ -252,17 +345,20 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		} else if (warp == kIssueWarp) {
 			// ================================================================================== issue warp
 			if (elect_one()) {
-				if (b > 0) // the weights were rewritten through the generic proxy (by other SMs) earlier in this launch
-					asm volatile("fence.proxy.async;" ::: "memory");
-				tma_prefetch_desc(&tm_w);
-				mbar_arrive_expect_tx(w_full, NRC_LAYERS * 8192);
-				for (int l = 0; l < NRC_LAYERS; ++l)
-					tma_load_2d(w_sm + l * 8192, &tm_w, 0, l * 64, w_full);
+				if (b == 0) {
+					tma_prefetch_desc(&tm_w);
+					mbar_arrive_expect_tx(w_full, NRC_LAYERS * 8192);
+					for (int l = 0; l < NRC_LAYERS; ++l)
+						tma_load_2d(w_sm + l * 8192, &tm_w, 0, l * 64, w_full);
+				}
 				if (IN_MODE == NRC_IN_ENCODED) {
 					mbar_arrive_expect_tx(in_full, 16384);
 					tma_load_2d(act_sm, &tm_in, 0, (int32_t)(blockIdx.x * NRC_TILE), in_full);
 				}
-				mbar_wait(w_full, w_loads & 1);
+				if (b == 0)
+					mbar_wait(w_full, 0);
+				else
+					mbar_wait(w_ready, w_reloads & 1);
 #pragma unroll 1
 				for (uint32_t j = 0; j < my_tiles; ++j) {
 					const uint32_t T = tile_base + j;
@@ -365,44 +461,15 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 						tgt[0] = t[0], tgt[1] = t[1], tgt[2] = t[2];
 					}
 				}
-				if (IN_MODE != NRC_IN_ENCODED) {
-					uint32_t o[16];
-#pragma unroll
-					for (int i = 0; i < 16; ++i)
-						o[i] = 0u; // nrc_gradient.comp:27-34: zero input + zero target => exactly zero contribution
-					if (IN_MODE == NRC_IN_PACKED) { // nrc_gradient.comp:29-31: UnpackNRCInput, then the same encoding
-						if (valid) {
-							float in[14];
-							uint32_t pk[4];
-							load_packed_input(p.in, gi, p.in_stride_bytes, pk);
-							unpack_nrc_input(p.scene, pk, in);
-							encode_nrc_half(in, h, o);
-						}
-					} else if (IN_MODE == NRC_IN_UNPACKED) {
-						if (valid) {
-							float in[14];
-							const float2 *src = (const float2 *)((const uint8_t *)p.in + gi * p.in_stride_bytes);
-#pragma unroll
-							for (int i = 0; i < 7; ++i) {
-								const float2 t = __ldg(src + i);
-								in[2 * i] = t.x, in[2 * i + 1] = t.y;
-							}
-							encode_nrc_half(in, h, o);
-						}
-					} else { // NRC_IN_IMAGE_RANDOM (gradient.comp:47-49)
-						uint32_t px = p.seed_x + (uint32_t)(gi % 128u), py = p.seed_y + (uint32_t)(gi / 128u);
-						pcg2d(px, py);
-						const float sc = 1.0f / (float)0xffffffffu;
-						const float u = sc * (float)px, v = sc * (float)py;
-						if (valid) {
-							if (h == 0)
-								sample_bilinear_rgb(p.image_rgba8, p.image_w, p.image_h, u, v, tgt);
-							encode_oneblob32_half(h ? v : u, o);
-						}
-					}
-					if (j > 0) // the previous tile's dW_0 MMA still reads a_0
-						mbar_wait(tile_done, (T - 1) & 1);
-					store_half_row(act_sm, o);
+				if (IN_MODE == NRC_IN_IMAGE_RANDOM && h == 0 && valid) { // target = the image at this sample's uv (gradient.comp:47-50)
+					uint32_t px = p.seed_x + (uint32_t)(gi % 128u), py = p.seed_y + (uint32_t)(gi / 128u);
+					pcg2d(px, py);
+					const float sc = 1.0f / (float)0xffffffffu;
+					sample_bilinear_rgb(p.image_rgba8, p.image_w, p.image_h, sc * (float)px, sc * (float)py, tgt);
+				}
+				if (IN_MODE != NRC_IN_ENCODED && j > 0) { // (tile 0 was encoded ahead of time)
+					mbar_wait(tile_done, (T - 1) & 1); // the previous tile's dW_0 MMA still reads a_0
+					encode_tile_row(p, n, tile);
 					arrive_a_ready();
 				}
 				NRC_GTRACE(3);
@@ -529,25 +596,27 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			}
 			NRC_GTRACE(8);
 		}
+		if (IN_MODE != NRC_IN_ENCODED && warp < kEpiWarps && tiles_next) { // encode the next batch's first tile now
+			if (my_tiles)
+				asm volatile("bar.sync 1, 256;" ::: "memory"); // every thread is done reading the staged dW_0 (a_0's tile)
+			encode_tile_row(tp.batch[b + 1], n_next, blockIdx.x);
+			arrive_a_ready();
+		}
 		tile_base += my_tiles;
-		w_loads += my_tiles ? 1u : 0u;
+		w_reloads += (b > 0 && my_tiles) ? 1u : 0u;
 
 		// ============================================================ deterministic reduction (+ optimizer step)
-		grid_sync(tp.grid_bar);
+		NrcOptimizerState pending_state{};
+		bool publish_pending = false;
+		grid_sync<false>(tp.grid_bar);
 		NRC_GTRACE(9);
 		{
 			const uint32_t num_partials = gridDim.x;
-			// the batch's record count: integers < 2^24, so any summation order is exact
-			float c = threadIdx.x < num_partials ? ld_cg(p.partials + (size_t)threadIdx.x * NRC_GRAD_STRIDE + NRC_GRAD_COUNT_SLOT) : 0.0f;
-#pragma unroll
-			for (int off = 16; off > 0; off >>= 1)
-				c += __shfl_xor_sync(0xffffffffu, c, off);
-			if (lane == 0)
-				scratch[warp] = c;
-			__syncthreads();
+			// the batch's record count: integers < 2^24, so any summation order is exact (the load is issued here, its
+			// reduction happens below, under the latency of the partial loads)
+			float cnt_part = threadIdx.x < num_partials ? ld_cg(p.partials + (size_t)threadIdx.x * NRC_GRAD_STRIDE + NRC_GRAD_COUNT_SLOT) : 0.0f;
 			float count = 0.0f;
-			for (int w = 0; w < kTrainThreads / 32; ++w)
-				count += scratch[w];
+			bool have_count = false;
 			NRC_GTRACE(0x50);
 			const int adam_mode = tp.adam_mode[b];
 			AdamParams adam = tp.adam;
@@ -589,6 +658,13 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							v[c][u] = blk < kReduceBlocks && pp < num_partials ? ld_cg4(src + (size_t)pp * NRC_GRAD_STRIDE) : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 						}
 					}
+					if (!have_count) { // block-wide sum of the per-CTA record counts (all threads < 256 take this path together)
+#pragma unroll
+						for (int off = 16; off > 0; off >>= 1)
+							cnt_part += __shfl_xor_sync(0xffffffffu, cnt_part, off);
+						if (lane == 0)
+							scratch[warp] = cnt_part;
+					}
 #pragma unroll
 					for (uint32_t c = 0; c < 3; ++c) {
 						float4 acc = v[c][0];
@@ -600,6 +676,11 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 				}
 				NRC_GTRACE(0x51);
 				__syncthreads();
+				if (!have_count) {
+					for (int w = 0; w < 8; ++w)
+						count += scratch[w];
+					have_count = true;
+				}
 				if (mine_blk) {
 					const float *col = &red_sm[threadIdx.x >> 6][0][(threadIdx.x & 63u) >> 2].x + (threadIdx.x & 3u);
 					float t[16];
@@ -658,12 +739,20 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 				const uint32_t cc = *p.d_count;
 				*p.d_count = cc < tp.batch_cap ? cc : tp.batch_cap;
 			}
-			if (adam_mode != 0 && __syncthreads_or(any_adam ? 1 : 0)) // (the batch was not empty; identical on every CTA)
-				publish_state_if_last(adam, st);
+			if (adam_mode != 0 && __syncthreads_or(any_adam ? 1 : 0)) { // (the batch was not empty; identical on every CTA)
+				if (b + 1 < tp.num_batches)
+					pending_state = st, publish_pending = true; // every CTA has read the old state once the next barrier is passed
+				else
+					publish_state_if_last(adam, st);
+			}
 		}
 		NRC_GTRACE(0x54);
-		if (b + 1 < tp.num_batches)
-			grid_sync(tp.grid_bar); // the next batch runs on the weights (and optimizer state) just written
+		if (b + 1 < tp.num_batches) {
+			grid_sync<false>(tp.grid_bar); // the next batch runs on the weights (and optimizer state) just written
+			if (publish_pending && blockIdx.x == 0 && threadIdx.x == 0)
+				*tp.adam.opt_state = pending_state; // read again only after the next batch's first grid barrier
+		}
+		n = n_next, my_tiles = tiles_next;
 	}
 #ifdef NRC_TRACE
 	NRC_GTRACE(10);
