@@ -76,6 +76,40 @@ def test_infer_packed_matches_oracle(nrc, oracle_mod, state):
     assert out_err(y, ref.astype(np.float32)) <= 1.0
 
 
+def test_full_size_record_inference_properties(nrc, oracle_mod):
+    """BASELINE config 3 size (1920x1080 queries) through the record input modes, where every CTA runs many tiles per slot and
+    the producer warps run several tiles ahead (buffer hand-offs in both directions): queries are independent, so a
+    permutation of the records permutes the outputs bit for bit; a random subset is checked against the oracle; the fused
+    path equals (bit for bit) the stand-alone unpack followed by the 14-float record path."""
+    n = 1920 * 1080
+    st = nrc.NrcState(0, (1920, 1080), seed=4)
+    w32 = he_weights(41)
+    st.set_weights(w32)
+    sc = make_scene(17)
+    dsc = upload_scene(nrc, sc)
+    g = torch.Generator(device="cuda").manual_seed(9)
+    pk = dev(random_packed_inputs(19, 8192, sc).view(np.int32))  # (int32 view: torch indexes no uint32 tensors)
+    pk = pk[torch.randint(0, 8192, (n,), device="cuda", generator=g)].contiguous()  # n records drawn from 8192 distinct ones
+    y = st.infer_packed(pk, dsc)
+    perm = torch.randperm(n, device="cuda", generator=g)
+    assert torch.equal(st.infer_packed(pk[perm].contiguous(), dsc), y[perm])
+    unp = nrc.unpack_inputs(pk, dsc)
+    yu = st.infer_unpacked(unp)
+    assert torch.equal(yu, y)
+    assert torch.equal(st.infer_unpacked(unp[perm].contiguous()), yu[perm])
+    idx = torch.randint(0, n, (2048,), device="cuda", generator=g)
+    sub = pk[idx].cpu().numpy().view(np.uint32)
+    ref = oracle_mod.evaluate(w32.astype(np.float16), oracle_mod.encode(oracle_mod.unpack(sc, sub)), oracle_mod.ACC_FP32, clamp=True)
+    assert out_err(y[idx].float().cpu().numpy(), ref.astype(np.float32)) <= 1.0
+    # ragged tail + device-resident count smaller than the buffer
+    m = n - 12345
+    cnt = torch.tensor([m], dtype=torch.int32, device="cuda")
+    out = torch.full((n, 3), -1.0, dtype=torch.float16, device="cuda")
+    st.infer_unpacked(unp, count=cnt, outputs=out)
+    assert torch.equal(out[:m], yu[:m]) and (out[m:] == -1).all()
+    st.close()
+
+
 def test_nrc_infer_eval_records_scatter(nrc, oracle_mod, state):
     """The full nrc_inference.comp pass on NRCEvalRecord[]: device count, invalid / screen / train destinations."""
     sc = make_scene(21)

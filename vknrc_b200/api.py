@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnrc_b200.so")
+# (NRC_B200_LIB: development override used by tools/lab_train.py to time a variant build of the same library)
+LIB_PATH = os.environ.get("NRC_B200_LIB") or os.path.join(_HERE, "libnrc_b200.so")
 
 WEIGHT_COUNT = 20672
 GRADIENT_FLOATS = 20736

@@ -32,10 +32,11 @@ def needs_build() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
-    if not force and not needs_build():
+def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str = LIB) -> str:
+    """`out` / `extra_flags`: development variants (tools/lab_train.py) built beside the product library."""
+    if out == LIB and not force and not needs_build():
         return LIB
-    objdir = os.path.join(HERE, "build")
+    objdir = os.path.join(HERE, "build") if out == LIB else out + ".obj"
     os.makedirs(objdir, exist_ok=True)
     env = dict(os.environ)
     env.pop("CC", None), env.pop("CXX", None)  # this image exports a gcc wrapper that nvcc must not pick up
@@ -47,12 +48,12 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
         objs.append(obj)
     log = []
     for src, p in procs:
-        out, _ = p.communicate()
-        log.append(out)
+        text, _ = p.communicate()
+        log.append(text)
         if p.returncode != 0:
-            sys.stderr.write(out)
+            sys.stderr.write(text)
             raise RuntimeError(f"nvcc failed on {src}")
-    link = [_nvcc(), "-shared", "-o", LIB, *objs, "-lcudart"]
+    link = [_nvcc(), "-shared", "-o", out, *objs, "-lcudart"]
     r = subprocess.run(link, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
     if r.returncode != 0:
         sys.stderr.write(r.stdout)
@@ -61,7 +62,7 @@ def build(force: bool = False, verbose: bool = False, extra_flags=()) -> str:
         f.write("\n".join(log))
     if verbose:
         print("\n".join(log))
-    return LIB
+    return out
 
 
 if __name__ == "__main__":

@@ -10,10 +10,15 @@
 //     Epilogue: thread = sample = TMEM lane: tcgen05.ld the accumulator row, ReLU + fp32->fp16 in one
 //     cvt.rn.relu.f16x2.f32 per pair, tcgen05.st it back as the next layer's A operand. Activations never leave
 //     TMEM. For record inputs the same threads run the input encoding and write A_0 directly.
-//   * pre-encoded inputs: every slot double-buffers its own 16 KB input tiles; its issuing thread re-arms a buffer
-//     with the tile after next as soon as the layer-0 MMA that read it has completed.
+//   * every slot double-buffers its own 16 KB input tiles (A_0, 128-byte-swizzled rows) in shared memory; layer 0 reads
+//     them SS-form. Pre-encoded inputs: the slot's issuing thread TMA-loads the tile after next as soon as the layer-0
+//     MMA that read a buffer has completed. Record inputs (14-float records, 16-byte packed records + scene gather,
+//     image grid): NP extra PRODUCER warps unpack + encode records ahead of the slots (a warp = a quarter tile at a
+//     time, up to two tiles ahead per slot) and write the encoded rows into the same buffers - the input encoding is
+//     fused into the first layer, and the gather / encode latency never sits in a slot's MMA -> epilogue chain.
 // Hand-offs: a 128-thread named barrier inside the slot (operand stored / accumulator drained -> issuer), the
-// mbarrier d_full[slot] (tcgen05.commit -> epilogue) and in_full[slot][2] (TMA -> layer-0 MMA).
+// mbarriers d_full[slot] (tcgen05.commit -> epilogue), in_full[slot][2] (TMA or 4 producer warps -> layer-0 MMA) and
+// in_free[slot][2] (layer 0 done -> producers).
 #include "nrc_kernels.h"
 #include "nrc_encode.cuh"
 #include "nrc_unpack.cuh"
@@ -42,17 +47,19 @@ __device__ unsigned int g_nrc_trace_n[4];
 
 namespace nrc {
 
-// Shared memory: weights (6 x 8 KB), then -- pre-encoded inputs only -- two 16 KB input buffers per slot, then barriers.
+// Shared memory: weights (6 x 8 KB), two 16 KB input buffers per slot, barriers.
 template <int NT, int IN_MODE> struct InferSmem {
 	static constexpr uint32_t kWeightBytes = NRC_LAYERS * 8192;
 	static constexpr uint32_t kInOff = kWeightBytes;
-	static constexpr uint32_t kInBytes = IN_MODE == NRC_IN_ENCODED ? NT * 2 * 16384 : 0;
+	static constexpr uint32_t kInBytes = NT * 2 * 16384;
 	static constexpr uint32_t kBarOff = kInOff + kInBytes;
+	static constexpr uint32_t kLutOff = kBarOff + 256; // sRGB -> linear table (packed records only)
+	static constexpr uint32_t kLutBytes = IN_MODE == NRC_IN_PACKED ? 1024 : 0;
 #ifdef NRC_TRACE
-	static constexpr uint32_t kTraceOff = kBarOff + 256;
+	static constexpr uint32_t kTraceOff = kLutOff + kLutBytes;
 	static constexpr uint32_t kBytes = kTraceOff + 4 * NRC_TRACE_CAP * 8 + 1024;
 #else
-	static constexpr uint32_t kBytes = kBarOff + 256 + 1024; // + slack for manual 1024 B alignment
+	static constexpr uint32_t kBytes = kLutOff + kLutBytes + 1024; // + slack for manual 1024 B alignment
 #endif
 };
 
@@ -94,16 +101,60 @@ __device__ __forceinline__ void write_result(const InferParams &p, uint64_t gi, 
 	}
 }
 
-template <int NT, int IN_MODE>
-__global__ void __launch_bounds__(NT * 128, 1)
+// ------------------------------------------------------------------------------------------------ producer warps
+// One unit of producer work = a quarter tile (32 records, one per lane): raw record -> 64 encoded features -> the
+// row's eight 16-byte chunks at their 128-byte-swizzle positions (exactly what TMA would have written).
+template <int IN_MODE> struct RawInput {
+	uint32_t pk[4]; // NRC_IN_PACKED
+	float2 f[7];    // NRC_IN_UNPACKED
+};
+template <int IN_MODE> __device__ __forceinline__ void load_raw(const InferParams &p, uint64_t gi, bool valid, RawInput<IN_MODE> &r) {
+	if (IN_MODE == NRC_IN_PACKED) {
+		r.pk[0] = r.pk[1] = r.pk[2] = r.pk[3] = 0u;
+		if (valid)
+			load_packed_input(p.in, gi, p.in_stride_bytes, r.pk);
+	} else if (IN_MODE == NRC_IN_UNPACKED) {
+		const float2 *src = (const float2 *)((const uint8_t *)p.in + gi * p.in_stride_bytes);
+#pragma unroll
+		for (int i = 0; i < 7; ++i)
+			r.f[i] = valid ? __ldg(src + i) : make_float2(0.0f, 0.0f);
+	}
+}
+template <int IN_MODE>
+__device__ __forceinline__ void encode_raw(const InferParams &p, uint64_t gi, bool valid, const RawInput<IN_MODE> &r, uint32_t o[32], const float *lut) {
+	if (IN_MODE == NRC_IN_IMAGE_GRID) { // uv = (coord + 0.5) / width  (inference.comp:33-34)
+		const uint32_t x = (uint32_t)(gi % p.image_width), y = (uint32_t)(gi / p.image_width);
+		encode_oneblob32(((float)x + 0.5f) / (float)p.image_width, ((float)y + 0.5f) / (float)p.image_width, o);
+		return;
+	}
+	float in[14];
+	if (IN_MODE == NRC_IN_PACKED) {
+		if (valid) {
+			unpack_nrc_input(p.scene, r.pk, in, lut);
+		} else {
+#pragma unroll
+			for (int i = 0; i < 14; ++i)
+				in[i] = 0.0f;
+		}
+	} else {
+#pragma unroll
+		for (int i = 0; i < 7; ++i)
+			in[2 * i] = r.f[i].x, in[2 * i + 1] = r.f[i].y;
+	}
+	encode_nrc(in, o);
+}
+
+template <int NT, int NP, int IN_MODE>
+__global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
     nrc_infer_kernel(const InferParams p, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_in) {
 	using L = InferSmem<NT, IN_MODE>;
+	static_assert((IN_MODE == NRC_IN_ENCODED) == (NP == 0), "producer warps exist exactly for the record input modes");
 	extern __shared__ uint8_t smem_raw[];
 	uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	uint8_t *w_sm = smem;
 	uint64_t *bars = (uint64_t *)(smem + L::kBarOff);
-	uint64_t *w_full = bars, *d_full = bars + 1, *in_full = d_full + NT; // in_full[slot][2]
-	uint32_t *tmem_slot = (uint32_t *)(in_full + 2 * NT);
+	uint64_t *w_full = bars, *d_full = bars + 1, *in_full = d_full + NT, *in_free = in_full + 2 * NT; // in_full / in_free [slot][2]
+	uint32_t *tmem_slot = (uint32_t *)(in_free + 2 * NT);
 #ifdef NRC_TRACE
 	uint2 *trace_sm = (uint2 *)(smem + L::kTraceOff);
 	uint32_t trace_n = 0;
@@ -122,10 +173,16 @@ __global__ void __launch_bounds__(NT * 128, 1)
 		return;
 	const uint32_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
+	const float *lut = (const float *)(smem + L::kLutOff);
+	if (IN_MODE == NRC_IN_PACKED && threadIdx.x < 256)
+		((float *)(smem + L::kLutOff))[threadIdx.x] = kSrgbToLinear[threadIdx.x];
 	if (threadIdx.x == 0) {
 		mbar_init(w_full, 1);
-		for (int i = 0; i < NT; ++i)
-			mbar_init(d_full + i, 1), mbar_init(in_full + 2 * i, 1), mbar_init(in_full + 2 * i + 1, 1);
+		for (int i = 0; i < NT; ++i) {
+			mbar_init(d_full + i, 1);
+			for (int b = 0; b < 2; ++b)
+				mbar_init(in_full + 2 * i + b, NP ? 4 : 1), mbar_init(in_free + 2 * i + b, 1);
+		}
 		fence_mbar_init();
 	}
 	if (warp == 0)
@@ -141,6 +198,40 @@ __global__ void __launch_bounds__(NT * 128, 1)
 			tma_load_2d(w_sm + l * 8192, &tm_w, 0, l * 64, w_full);
 	}
 
+	if (NP > 0 && warp >= NT * 4) {
+		// ------------------------------------------------------------------------------------------ producer warps
+		// unit u = quarter (u & 3) of the CTA's tile g = u >> 2, which slot g % NT runs as its (g / NT)-th tile from
+		// buffer (g / NT) & 1. Units repeat their (slot, buffer, quarter) with period 8 NT; a producer warp owns a fixed
+		// set of those combinations (NP divides 8 NT), so it meets the uses of one buffer in order and a parity wait on
+		// in_free can never be a whole phase behind. The raw record of the warp's next unit is fetched before the
+		// current one is processed.
+		static_assert((8 * NT) % (NP ? NP : 1) == 0, "the producer warps must tile the (slot, buffer, quarter) combinations evenly");
+		const uint32_t pw = warp - NT * 4, units = 4 * my_tiles;
+		auto unit_gi = [&](uint32_t u) { return (uint64_t)(blockIdx.x + (u >> 2) * gridDim.x) * NRC_TILE + (u & 3u) * 32 + lane; };
+		RawInput<IN_MODE> raw, raw_next;
+		if (pw < units)
+			load_raw<IN_MODE>(p, unit_gi(pw), unit_gi(pw) < n, raw);
+#pragma unroll 1
+		for (uint32_t u = pw; u < units; u += NP) {
+			const uint32_t g = u >> 2, s = g % NT, it = g / NT, b = it & 1u, row = (u & 3u) * 32 + lane;
+			const uint64_t gi = unit_gi(u);
+			if (u + NP < units)
+				load_raw<IN_MODE>(p, unit_gi(u + NP), unit_gi(u + NP) < n, raw_next);
+			uint32_t o[32];
+			encode_raw<IN_MODE>(p, gi, gi < n, raw, o, lut);
+			if (it >= 2) // the slot has finished layer 0 of the tile that used this buffer before
+				mbar_wait(in_free + 2 * s + b, ((it >> 1) - 1) & 1);
+			uint8_t *dst = smem + L::kInOff + (s * 2 + b) * 16384 + row * 128;
+#pragma unroll
+			for (int c = 0; c < 8; ++c)
+				*(uint4 *)(dst + ((c ^ (row & 7)) << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+			fence_proxy_async_smem(); // generic-proxy stores -> visible to the MMA's async-proxy operand reads
+			__syncwarp();
+			if (lane == 0)
+				mbar_arrive(in_full + 2 * s + b);
+			raw = raw_next;
+		}
+	} else {
 	// ---------------------------------------------------------------------------------------------- slot warpgroups
 	// Each slot is self-contained: its 128 threads run the epilogues, and one elected thread of ONE of its warps issues
 	// the slot's tcgen05.mma (and, for pre-encoded inputs, the TMA loads of the slot's own double-buffered input tiles).
@@ -150,7 +241,7 @@ __global__ void __launch_bounds__(NT * 128, 1)
 	const uint32_t d_col = tmem + s * 96, a_col = d_col + 64;             // issuer's view (lane 0)
 	const uint32_t d_t = tmem_addr(tmem, q * 32, s * 96), a_t = d_t + 64; // this warp's 32 lanes
 	uint8_t *in_sm = smem + L::kInOff + s * 2 * 16384;
-	uint64_t *my_in_full = in_full + 2 * s, *my_d_full = d_full + s;
+	uint64_t *my_in_full = in_full + 2 * s, *my_in_free = in_free + 2 * s, *my_d_full = d_full + s;
 #ifdef NRC_INFER_F16ACC
 	constexpr uint32_t idesc64 = make_idesc_f16_f16(128, 64, false, false);
 	constexpr uint32_t idesc16 = make_idesc_f16_f16(128, 16, false, false);
@@ -193,35 +284,6 @@ __global__ void __launch_bounds__(NT * 128, 1)
 		const uint32_t tile = blockIdx.x + j * gridDim.x;
 		const uint64_t gi = (uint64_t)tile * NRC_TILE + row;
 		const bool valid = gi < n;
-		if (IN_MODE != NRC_IN_ENCODED) {
-			uint32_t o[32];
-			if (IN_MODE == NRC_IN_UNPACKED || IN_MODE == NRC_IN_PACKED) {
-				float in[14];
-				if (valid && IN_MODE == NRC_IN_PACKED) {
-					uint32_t pk[4];
-					load_packed_input(p.in, gi, p.in_stride_bytes, pk);
-					unpack_nrc_input(p.scene, pk, in);
-				} else if (valid) {
-					const float2 *src = (const float2 *)((const uint8_t *)p.in + gi * p.in_stride_bytes);
-#pragma unroll
-					for (int i = 0; i < 7; ++i) {
-						const float2 t = __ldg(src + i);
-						in[2 * i] = t.x, in[2 * i + 1] = t.y;
-					}
-				} else {
-#pragma unroll
-					for (int i = 0; i < 14; ++i)
-						in[i] = 0.0f;
-				}
-				encode_nrc(in, o);
-			} else { // NRC_IN_IMAGE_GRID: uv = (coord + 0.5) / width  (inference.comp:33-34)
-				const uint32_t x = (uint32_t)(gi % p.image_width), y = (uint32_t)(gi / p.image_width);
-				encode_oneblob32(((float)x + 0.5f) / (float)p.image_width, ((float)y + 0.5f) / (float)p.image_width, o);
-			}
-			tmem_st_x32(a_t, o);
-			tc_wait_st();
-			slot_sync();
-		}
 		uint32_t b_lo = w_lo; // descriptor (low word) of W_l, advanced by one 8 KB matrix per layer
 #ifdef NRC_INFER_NO_UNROLL
 #pragma unroll 1
@@ -235,7 +297,7 @@ __global__ void __launch_bounds__(NT * 128, 1)
 				if (elect_one()) {
 					tc_fence_after();
 					NRC_TRACE_EV(s, NRC_TRACE_TAG(6));
-					if (IN_MODE == NRC_IN_ENCODED && l == 0) {
+					if (l == 0) { // A_0 from the slot's input buffer (TMA or producer warps), SS form
 						mbar_wait(my_in_full + (it & 1), (it >> 1) & 1);
 						const uint32_t a_lo = in_lo + (it & 1) * (16384 >> 4);
 #pragma unroll
@@ -249,8 +311,14 @@ __global__ void __launch_bounds__(NT * 128, 1)
 					NRC_TRACE_EV(s, NRC_TRACE_TAG(7));
 					tc_commit(my_d_full);
 					// layer 0 has consumed input buffer (it & 1) (its completion was observed below, one layer ago)
-					if (IN_MODE == NRC_IN_ENCODED && l == 1 && it + 2 < slot_tiles)
-						load_input_tile(it + 2);
+					if (l == 1) {
+						if (IN_MODE == NRC_IN_ENCODED) {
+							if (it + 2 < slot_tiles)
+								load_input_tile(it + 2);
+						} else {
+							mbar_arrive(my_in_free + (it & 1));
+						}
+					}
 					NRC_TRACE_EV(s, NRC_TRACE_TAG(0));
 				}
 				__syncwarp();
@@ -282,8 +350,7 @@ __global__ void __launch_bounds__(NT * 128, 1)
 				uint32_t y[4];
 				tmem_ld_x4(d_t, y);
 				tc_wait_ld();
-				if (IN_MODE == NRC_IN_ENCODED)
-					slot_sync();
+				slot_sync();
 				pend = valid, pend_gi = gi;
 				pend_y0 = __half2float(__ushort_as_half((unsigned short)y[0])), pend_y1 = __half2float(__ushort_as_half((unsigned short)y[1]));
 				pend_y2 = __half2float(__ushort_as_half((unsigned short)y[2]));
@@ -294,19 +361,32 @@ __global__ void __launch_bounds__(NT * 128, 1)
 			}
 #else
 			if (l < NRC_HIDDEN_LAYERS) {
-				uint32_t v[64], o[32];
-				tmem_ld_x32(d_t, v);
-				tmem_ld_x32(d_t + 32, v + 32);
-				tc_wait_ld();
+				if (NP > 0) { // (1024-thread CTA, 64 registers: the row in two halves)
 #pragma unroll
-				for (int i = 0; i < 16; ++i)
-					o[i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-				tmem_st_x16(a_t, o);
+					for (int hh = 0; hh < 2; ++hh) {
+						uint32_t v[32], o[16];
+						tmem_ld_x32(d_t + 32 * hh, v);
+						tc_wait_ld();
 #pragma unroll
-				for (int i = 16; i < 32; ++i)
-					o[i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-				NRC_TRACE_EV(s, NRC_TRACE_TAG(4));
-				tmem_st_x16(a_t + 16, o + 16);
+						for (int i = 0; i < 16; ++i)
+							o[i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+						tmem_st_x16(a_t + 16 * hh, o);
+					}
+				} else {
+					uint32_t v[64], o[32];
+					tmem_ld_x32(d_t, v);
+					tmem_ld_x32(d_t + 32, v + 32);
+					tc_wait_ld();
+#pragma unroll
+					for (int i = 0; i < 16; ++i)
+						o[i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+					tmem_st_x16(a_t, o);
+#pragma unroll
+					for (int i = 16; i < 32; ++i)
+						o[i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+					NRC_TRACE_EV(s, NRC_TRACE_TAG(4));
+					tmem_st_x16(a_t + 16, o + 16);
+				}
 				tc_wait_st();
 				NRC_TRACE_EV(s, NRC_TRACE_TAG(5));
 				slot_sync();
@@ -314,8 +394,7 @@ __global__ void __launch_bounds__(NT * 128, 1)
 				uint32_t y[4];
 				tmem_ld_x4(d_t, y);
 				tc_wait_ld();
-				if (IN_MODE == NRC_IN_ENCODED)
-					slot_sync(); // accumulator drained before the next tile's layer 0 overwrites it
+				slot_sync(); // accumulator drained before the next tile's layer 0 overwrites it
 				pend = valid, pend_gi = gi;
 				pend_y0 = __uint_as_float(y[0]), pend_y1 = __uint_as_float(y[1]), pend_y2 = __uint_as_float(y[2]);
 				if (NRC_INFER_FLUSH_LAYER < 0 && pend) {
@@ -335,14 +414,15 @@ __global__ void __launch_bounds__(NT * 128, 1)
 		g_nrc_trace_n[threadIdx.x >> 7] = trace_n;
 	}
 #endif
+	}
 	tc_fence_before();
 	__syncthreads();
 	if (warp == 0)
 		tmem_dealloc(tmem, 512);
 }
 
-template <int NT, int IN_MODE> static cudaError_t launch(const InferParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream) {
-	auto kern = nrc_infer_kernel<NT, IN_MODE>;
+template <int NT, int NP, int IN_MODE> static cudaError_t launch(const InferParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream) {
+	auto kern = nrc_infer_kernel<NT, NP, IN_MODE>;
 	constexpr uint32_t smem_bytes = InferSmem<NT, IN_MODE>::kBytes;
 	static bool configured = false;
 	if (!configured) {
@@ -353,7 +433,7 @@ template <int NT, int IN_MODE> static cudaError_t launch(const InferParams &p, c
 	}
 	const uint64_t ntiles = (p.n + NRC_TILE - 1) / NRC_TILE;
 	const uint32_t grid = (uint32_t)(ntiles < (uint64_t)sms ? ntiles : (uint64_t)sms);
-	kern<<<grid, NT * 128, smem_bytes, stream>>>(p, tm_w, tm_in);
+	kern<<<grid, (NT * 4 + NP) * 32, smem_bytes, stream>>>(p, tm_w, tm_in);
 	return cudaGetLastError();
 }
 
@@ -382,16 +462,16 @@ cudaError_t launch_unpack(const void *packed, uint32_t stride_bytes, uint64_t n,
 cudaError_t launch_infer(const InferParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream) {
 	if (p.n == 0)
 		return cudaSuccess;
-	constexpr int NT = NRC_INFER_SLOTS;
+	constexpr int NT = NRC_INFER_SLOTS, NTP = NRC_INFER_SLOTS_REC, NP = NRC_INFER_PRODUCER_WARPS;
 	switch (p.in_mode) {
 	case NRC_IN_ENCODED:
-		return launch<NT, NRC_IN_ENCODED>(p, tm_w, tm_in, sms, stream);
+		return launch<NT, 0, NRC_IN_ENCODED>(p, tm_w, tm_in, sms, stream);
 	case NRC_IN_UNPACKED:
-		return launch<NT, NRC_IN_UNPACKED>(p, tm_w, tm_in, sms, stream);
+		return launch<NTP, NP, NRC_IN_UNPACKED>(p, tm_w, tm_in, sms, stream);
 	case NRC_IN_IMAGE_GRID:
-		return launch<NT, NRC_IN_IMAGE_GRID>(p, tm_w, tm_in, sms, stream);
+		return launch<NTP, NP, NRC_IN_IMAGE_GRID>(p, tm_w, tm_in, sms, stream);
 	case NRC_IN_PACKED:
-		return launch<NT, NRC_IN_PACKED>(p, tm_w, tm_in, sms, stream);
+		return launch<NTP, NP, NRC_IN_PACKED>(p, tm_w, tm_in, sms, stream);
 	}
 	return cudaErrorInvalidValue;
 }

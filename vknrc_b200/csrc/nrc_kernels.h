@@ -10,6 +10,15 @@
 #ifndef NRC_INFER_SLOTS
 #define NRC_INFER_SLOTS 5 // 128-sample tiles in flight per SM: 5 x (64 accumulator + 32 operand) = 480 of 512 TMEM columns
 #endif
+// record input modes: slots + producer warps (unpack / encode ahead of the slots) share the 32 warps of a CTA
+// (measured at 1080p, unpacked / packed+scatter: 4+16: 94 / 207 us, 4+8: 102 / 259 us, 5+10: 107 / 278 us; before the
+// producer warps existed, 5 slots doing their own unpack + encode: 113 / 241 us)
+#ifndef NRC_INFER_SLOTS_REC
+#define NRC_INFER_SLOTS_REC 4
+#endif
+#ifndef NRC_INFER_PRODUCER_WARPS
+#define NRC_INFER_PRODUCER_WARPS 16 // must divide 8 * NRC_INFER_SLOTS_REC
+#endif
 
 namespace nrc {
 

@@ -176,6 +176,7 @@ __device__ __forceinline__ float4 ld_cg4(const float *p) {
 	return v;
 }
 
+// (168 registers: the register file is per SM sub-partition, 16384 each, and one of the four hosts 3 of the 9 warps)
 template <int IN_MODE>
 __global__ void __launch_bounds__(kTrainThreads, 1)
     nrc_train_kernel(const TrainParams tp, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_in) {
@@ -195,7 +196,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	NRC_GTRACE(1);
 
 	// epilogue warps 0..7: q = TMEM lane quarter (rows 32q..32q+31), h = which 32-column half of the 64-wide row
-	const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, q = warp & 3, h = (warp >> 2) & 1;
+	// (warp index through a shuffle: provably warp-uniform, so TMEM addresses / descriptors live in uniform registers)
+	const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31, q = warp & 3, h = (warp >> 2) & 1;
 	const uint32_t row = q * 32 + lane;
 
 	if (threadIdx.x == 0) {
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
-	const uint32_t tmem = *tmem_slot;
+	const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
 	NRC_GTRACE(2);
 
 	constexpr uint32_t id_fwd64 = make_idesc_f16_f32(128, 64, false, false);
@@ -217,9 +219,9 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	constexpr uint32_t id_dw64 = make_idesc_f16_f32(64, 64, true, true);  // A = delta MN-major, B = act MN-major
 	constexpr uint32_t id_dw5t = make_idesc_f16_f32(64, 16, true, true);  // dW_5^T: A = a_5 MN-major, B = delta_5 MN-major
 	// UMMA descriptors differ only in the start-address field: desc(addr + off) = desc(addr) + (off >> 4)
-	const uint64_t w_desc = make_smem_desc_sw128(smem_u32(w_sm), 0, 1024);
-	const uint64_t act_desc = make_smem_desc_sw128(smem_u32(act_sm), 0, 1024);
-	const uint64_t del_desc = make_smem_desc_sw128(smem_u32(delta_sm), 0, 1024);
+	// (only the start-address field = the low word varies; see mma_ss_lh)
+	const uint32_t w_desc = smem_desc_lo(smem_u32(w_sm)), act_desc = smem_desc_lo(smem_u32(act_sm)), del_desc = smem_desc_lo(smem_u32(delta_sm));
+	constexpr uint32_t dhi = kSmemDescHiSw128;
 	const uint32_t d_issue = tmem + kColWork;                           // issuer's view of the working accumulator
 	const uint32_t d_mine = tmem_addr(tmem, q * 32, kColWork + 32 * h); // this thread's 32 columns of its row
 
@@ -362,7 +364,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 #pragma unroll 1
 				for (uint32_t j = 0; j < my_tiles; ++j) {
 					const uint32_t T = tile_base + j;
-#pragma unroll 1
+#pragma unroll
 					for (int l = 0; l < NRC_LAYERS; ++l) { // ---- forward
 						if (IN_MODE == NRC_IN_ENCODED && l == 0) {
 							mbar_wait(in_full, T & 1);
@@ -371,37 +373,37 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							ar_ph ^= 1;
 						}
 						tc_fence_after();
-						const uint64_t a_d = act_desc + (uint32_t)(l * (16384 >> 4)), b_d = w_desc + (uint32_t)(l * (8192 >> 4));
+						const uint32_t a_d = act_desc + (uint32_t)(l * (16384 >> 4)), b_d = w_desc + (uint32_t)(l * (8192 >> 4));
 #pragma unroll
 						for (int k = 0; k < 4; ++k)
-							mma_ss(d_issue, a_d + k * 2, b_d + k * 2, l < 5 ? id_fwd64 : id_fwd16, k > 0);
+							mma_ss_lh(d_issue, a_d + k * 2, b_d + k * 2, dhi, l < 5 ? id_fwd64 : id_fwd16, k > 0);
 						tc_commit(d_full);
 					}
 					// ---- backward, per layer: dA first (critical path: delta_{l-1} = (delta_l W_l) * [a_l > 0]), then
 					// dW_l += delta_l^T a_l, which the tensor pipe executes while the epilogue of dA runs.
-#pragma unroll 1
+#pragma unroll
 					for (int l = 5; l >= 0; --l) {
 						mbar_wait(a_ready, ar_ph); // delta_l stored
 						ar_ph ^= 1;
 						tc_fence_after();
-						const uint64_t dl = del_desc + (uint32_t)(((5 - l) & 1) * (16384 >> 4));
-						const uint64_t al = act_desc + (uint32_t)(l * (16384 >> 4)), wl = w_desc + (uint32_t)(l * (8192 >> 4));
+						const uint32_t dl = del_desc + (uint32_t)(((5 - l) & 1) * (16384 >> 4));
+						const uint32_t al = act_desc + (uint32_t)(l * (16384 >> 4)), wl = w_desc + (uint32_t)(l * (8192 >> 4));
 						if (l == 5) {
-							mma_ss(d_issue, dl, wl, id_da, 0);
+							mma_ss_lh(d_issue, dl, wl, dhi, id_da, 0);
 							tc_commit(d_full);
 #pragma unroll
 							for (int k = 0; k < 8; ++k)
-								mma_ss(tmem + kColDW5, al + k * 128, dl + k * 128, id_dw5t, (j > 0) || (k > 0));
+								mma_ss_lh(tmem + kColDW5, al + k * 128, dl + k * 128, dhi, id_dw5t, (j > 0) || (k > 0));
 						} else {
 							if (l > 0) {
 #pragma unroll
 								for (int k = 0; k < 4; ++k)
-									mma_ss(d_issue, dl + k * 2, wl + k * 128, id_da, k > 0);
+									mma_ss_lh(d_issue, dl + k * 2, wl + k * 128, dhi, id_da, k > 0);
 								tc_commit(d_full);
 							}
 #pragma unroll
 							for (int k = 0; k < 8; ++k)
-								mma_ss(tmem + 64 * l, dl + k * 128, al + k * 128, id_dw64, (j > 0) || (k > 0));
+								mma_ss_lh(tmem + 64 * l, dl + k * 128, al + k * 128, dhi, id_dw64, (j > 0) || (k > 0));
 							if (l == 0) {
 								tc_commit(tile_done);
 								if (IN_MODE == NRC_IN_ENCODED && j + 1 < my_tiles) { // a_0 is free once dW_0 has consumed it
@@ -474,7 +476,11 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 				}
 				NRC_GTRACE(3);
 				// -------------------------------------------------------------------------------------- forward
+#ifdef NRC_TRAIN_NO_EPI_UNROLL
 #pragma unroll 1
+#else
+#pragma unroll
+#endif
 				for (int l = 0; l < NRC_LAYERS; ++l) {
 					mbar_wait(d_full, d_ph);
 					d_ph ^= 1;
@@ -523,7 +529,11 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 					arrive_a_ready();
 				}
 				// -------------------------------------------------------------------------------------- backward
+#ifdef NRC_TRAIN_NO_EPI_UNROLL
 #pragma unroll 1
+#else
+#pragma unroll
+#endif
 				for (int l = 5; l >= 1; --l) { // delta_{l-1} = fp16(D) * [a_l > 0], NaN -> 0 (NN_nv.glsl:198-220, 240-242)
 					mbar_wait(d_full, d_ph);
 					d_ph ^= 1;

@@ -46,9 +46,9 @@ __device__ const float kSrgbToLinear[256] = {
 	0.871367097f, 0.8796224f, 0.887923121f, 0.896269381f, 0.904661179f, 0.913098633f, 0.921581864f, 0.930110872f,
 	0.938685715f, 0.947306514f, 0.955973327f, 0.964686275f, 0.973445296f, 0.982250571f, 0.991102099f, 1.0f,
 };
-__device__ __forceinline__ float srgb_to_linear(uint32_t c8) { return __ldg(kSrgbToLinear + c8); }
-
-__device__ __forceinline__ void sample_texture_srgb_repeat(const NrcTexture *tex, float u, float v, float rgb[3]) {
+// `lut` = the table above or a copy of it in shared memory (the fused kernels stage it once per CTA: 24 look-ups per
+// textured record are 24 scattered L1 requests from global memory, but cheap LDS from shared memory)
+__device__ __forceinline__ void sample_texture_srgb_repeat(const NrcTexture *tex, float u, float v, float rgb[3], const float *lut) {
 	const uint32_t *p = (const uint32_t *)tex->texels_rgba8_srgb;
 	const int w = (int)tex->width, h = (int)tex->height;
 	const float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
@@ -59,13 +59,13 @@ __device__ __forceinline__ void sample_texture_srgb_repeat(const NrcTexture *tex
 	const uint32_t c00 = __ldg(p + y0 * w + x0), c10 = __ldg(p + y0 * w + x1), c01 = __ldg(p + y1 * w + x0), c11 = __ldg(p + y1 * w + x1);
 #pragma unroll
 	for (int c = 0; c < 3; ++c) {
-		const float a = srgb_to_linear((c00 >> (8 * c)) & 255u), b = srgb_to_linear((c10 >> (8 * c)) & 255u);
-		const float d = srgb_to_linear((c01 >> (8 * c)) & 255u), e = srgb_to_linear((c11 >> (8 * c)) & 255u);
+		const float a = lut[(c00 >> (8 * c)) & 255u], b = lut[(c10 >> (8 * c)) & 255u];
+		const float d = lut[(c01 >> (8 * c)) & 255u], e = lut[(c11 >> (8 * c)) & 255u];
 		rgb[c] = (a * (1.0f - tx) + b * tx) * (1.0f - ty) + (d * (1.0f - tx) + e * tx) * ty;
 	}
 }
 
-__device__ __forceinline__ void unpack_nrc_input(const NrcScene &sc, const uint32_t pk[4], float out[14]) {
+__device__ __forceinline__ void unpack_nrc_input(const NrcScene &sc, const uint32_t pk[4], float out[14], const float *lut = kSrgbToLinear) {
 	const uint32_t prim = pk[0], instance = pk[1] & 0x7FFFFFFFu;
 	const bool flip = (pk[1] >> 31) != 0u;
 	const float4 *m = (const float4 *)sc.transforms + 3 * (size_t)instance; // vec4(v, 1) * mat3x4 = a dot product per column
@@ -103,9 +103,9 @@ __device__ __forceinline__ void unpack_nrc_input(const NrcScene &sc, const uint3
 	const uint32_t dtex = __float_as_uint(md.w), stex = __float_as_uint(ms.w);
 	out[8] = md.x, out[9] = md.y, out[10] = md.z, out[11] = ms.x, out[12] = ms.y, out[13] = ms.z;
 	if (dtex != 0xFFFFFFFFu) // GetSceneDiffuse / GetSceneSpecular (Scene.glsl:59-64)
-		sample_texture_srgb_repeat(sc.textures + dtex, u, w, out + 8);
+		sample_texture_srgb_repeat(sc.textures + dtex, u, w, out + 8, lut);
 	if (stex != 0xFFFFFFFFu)
-		sample_texture_srgb_repeat(sc.textures + stex, u, w, out + 11);
+		sample_texture_srgb_repeat(sc.textures + stex, u, w, out + 11, lut);
 }
 
 __device__ __forceinline__ void load_packed_input(const void *base, uint64_t index, uint32_t stride_bytes, uint32_t pk[4]) {
