@@ -90,6 +90,12 @@ int nrc_mlp_gradient_encoded(const void *d_weights, float *d_dw, const void *d_i
  * `d_count` may be NULL (then max_count queries run). */
 int nrc_infer_encoded(nrc_handle_t h, const void *d_inputs, void *d_outputs_f16vec3, uint64_t n, int clamp_output,
                       void *stream);
+/* The same call on HOST buffers: what the reference's harness does around one launch - cudaMemcpy inputs up, launch,
+ * cudaMemcpy outputs down (test/main.cpp:103-128) - as one call. The queries are cut in chunks whose host->device copy,
+ * MLP and device->host copy overlap on three streams; the work is ordered after what `stream` holds at the call and
+ * `stream` completes when the outputs are in `h_outputs`. Pinned host memory makes the copies truly asynchronous. */
+int nrc_infer_encoded_host(nrc_handle_t h, const void *h_inputs, void *h_outputs_f16vec3, uint64_t n, int clamp_output,
+                           void *stream);
 /* records = 14 fp32 each (UnpackedNRCInput order, NRCRecord.glsl:40-45) `stride_bytes` apart; outputs max(y,0) fp16x3 */
 int nrc_infer_unpacked(nrc_handle_t h, const void *d_records, uint32_t stride_bytes, const uint32_t *d_count,
                        uint64_t max_count, void *d_outputs_f16vec3, void *stream);

@@ -50,6 +50,23 @@ def test_evaluate_encoded_matches_golden_reference_outputs(nrc, golden):
     assert np.isfinite(yu).all() and np.abs(yu - golden["ref_evaluate_uniform"].astype(np.float32)).max() < 1e-6
 
 
+def test_infer_encoded_host_equals_device_path(nrc):
+    """nrc_infer_encoded_host (host buffers, chunked copy / compute overlap) returns bit for bit what the device-buffer
+    call returns, for sizes below, at and far above one chunk per tile, pinned and pageable host memory."""
+    st = nrc.NrcState(0, (64, 48), seed=21)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for n, pinned in ((1, True), (127, False), (1025, True), (300000, True), (70001, False)):
+        x = torch.rand((n, 64), device="cuda", generator=g).half()
+        ref = st.infer_encoded(x, clamp=True)
+        hx = x.cpu().pin_memory() if pinned else x.cpu()
+        hy = torch.full((n, 3), -1.0, dtype=torch.float16)
+        hy = hy.pin_memory() if pinned else hy
+        st.infer_encoded_host(hx, hy, clamp=True)
+        torch.cuda.synchronize()
+        assert torch.equal(hy, ref.cpu())
+    st.close()
+
+
 def test_evaluate_empty_and_determinism(nrc):
     w = dev(he_weights(3).astype(np.float16))
     out = nrc.mlp_evaluate_encoded(w, torch.empty((0, 64), dtype=torch.float16, device="cuda"))

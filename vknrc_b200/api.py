@@ -136,6 +136,7 @@ SIGNATURES = {
     "nrc_set_prediction_capture": (None, [C.c_void_p, C.c_void_p]),
     "nrc_image_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.c_float, C.c_void_p]),
+    "nrc_infer_encoded_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
     "nrc_image_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
 }
 
@@ -300,6 +301,14 @@ class NrcState:
             outputs = torch.empty((n, 3), dtype=torch.float16, device=inputs.device)
         _check(lib().nrc_infer_encoded(self._h, _ptr(inputs), _ptr(outputs), n, int(clamp), _stream()))
         return outputs
+
+    def infer_encoded_host(self, h_inputs, h_outputs, clamp: bool = False):
+        """nrc_infer_encoded_host: pre-encoded queries in (pinned) HOST memory -> outputs in host memory, copies pipelined with
+        the MLP inside the call (the reference harness' cudaMemcpy / launchKernel / cudaMemcpy, test/main.cpp:103-128)."""
+        assert not h_inputs.is_cuda and not h_outputs.is_cuda and h_inputs.is_contiguous() and h_outputs.is_contiguous()
+        n = h_inputs.shape[0]
+        _check(lib().nrc_infer_encoded_host(self._h, h_inputs.data_ptr(), h_outputs.data_ptr(), n, int(clamp), _stream()))
+        return h_outputs
 
     def infer_unpacked(self, records, count=None, outputs=None, stride_bytes: int = 56, max_count=None):
         import torch

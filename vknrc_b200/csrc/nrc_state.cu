@@ -129,6 +129,12 @@ NrcState::NrcState(int device, Extent2D extent, uint64_t seed) : m_device(device
 NrcState::~NrcState() {
 	cudaFree(m_weights), cudaFree(m_use_weights), cudaFree(m_optimizer_state), cudaFree(m_optimizer_entries);
 	cudaFree(m_gradients), cudaFree(m_partials), cudaFree(m_sync_words);
+	cudaFree(m_stage_in), cudaFree(m_stage_out);
+	if (m_stream_in) {
+		cudaStreamDestroy(m_stream_in), cudaStreamDestroy(m_stream_out), cudaEventDestroy(m_ev_start), cudaEventDestroy(m_ev_out);
+		for (int c = 0; c < kHostChunks; ++c)
+			cudaEventDestroy(m_ev_in[c]), cudaEventDestroy(m_ev_done[c]);
+	}
 	CommShutdown();
 }
 
@@ -236,6 +242,62 @@ int NrcState::Infer(InferParams p, const void *encoded_inputs, const __half *wei
 		return fail(rc, err);
 	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
 	NRC_CUDA_TRY(launch_infer(p, tm_w, tm_in, m_sms, stream), sink);
+	return NRC_OK;
+}
+
+int NrcState::InferEncodedHost(const void *h_inputs, void *h_outputs, uint64_t n, int clamp_output, const __half *weights, cudaStream_t stream) {
+	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
+	if (n == 0)
+		return NRC_OK;
+	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
+	if (!m_stream_in) {
+		NRC_CUDA_TRY(cudaStreamCreateWithFlags(&m_stream_in, cudaStreamNonBlocking), sink);
+		NRC_CUDA_TRY(cudaStreamCreateWithFlags(&m_stream_out, cudaStreamNonBlocking), sink);
+		NRC_CUDA_TRY(cudaEventCreateWithFlags(&m_ev_start, cudaEventDisableTiming), sink);
+		NRC_CUDA_TRY(cudaEventCreateWithFlags(&m_ev_out, cudaEventDisableTiming), sink);
+		for (int c = 0; c < kHostChunks; ++c) {
+			NRC_CUDA_TRY(cudaEventCreateWithFlags(&m_ev_in[c], cudaEventDisableTiming), sink);
+			NRC_CUDA_TRY(cudaEventCreateWithFlags(&m_ev_done[c], cudaEventDisableTiming), sink);
+		}
+	}
+	if (n > m_stage_capacity) { // (re-allocation synchronises the device: a one-time cost per size)
+		cudaFree(m_stage_in), cudaFree(m_stage_out);
+		m_stage_in = m_stage_out = nullptr, m_stage_capacity = 0;
+		NRC_CUDA_TRY(cudaMalloc(&m_stage_in, n * 128), sink);
+		NRC_CUDA_TRY(cudaMalloc(&m_stage_out, n * 6), sink);
+		m_stage_capacity = n;
+	}
+	CUtensorMap tm_w, tm_in;
+	std::string err;
+	int rc = make_weight_tensor_map(&tm_w, weights, &err);
+	if (rc != NRC_OK)
+		return fail(rc, err);
+	// equal chunks of whole 128-query tiles (the host -> device copies are the long pole: everything else hides under them)
+	const uint64_t tiles = (n + NRC_TILE - 1) / NRC_TILE;
+	const int chunks = (int)(tiles < (uint64_t)kHostChunks ? tiles : (uint64_t)kHostChunks);
+	NRC_CUDA_TRY(cudaEventRecord(m_ev_start, stream), sink);
+	NRC_CUDA_TRY(cudaStreamWaitEvent(m_stream_in, m_ev_start, 0), sink);
+	NRC_CUDA_TRY(cudaStreamWaitEvent(m_stream_out, m_ev_start, 0), sink);
+	uint64_t first = 0;
+	for (int c = 0; c < chunks; ++c) {
+		const uint64_t last_tile = tiles * (uint64_t)(c + 1) / (uint64_t)chunks;
+		const uint64_t end = last_tile * NRC_TILE < n ? last_tile * NRC_TILE : n, cnt = end - first;
+		NRC_CUDA_TRY(cudaMemcpyAsync((uint8_t *)m_stage_in + first * 128, (const uint8_t *)h_inputs + first * 128, cnt * 128, cudaMemcpyHostToDevice, m_stream_in), sink);
+		NRC_CUDA_TRY(cudaEventRecord(m_ev_in[c], m_stream_in), sink);
+		NRC_CUDA_TRY(cudaStreamWaitEvent(stream, m_ev_in[c], 0), sink);
+		InferParams p{};
+		p.n = cnt, p.in_mode = NRC_IN_ENCODED, p.out_mode = NRC_OUT_F16VEC3, p.clamp_output = clamp_output, p.out = (uint8_t *)m_stage_out + first * 6;
+		rc = make_input_tensor_map(&tm_in, (const uint8_t *)m_stage_in + first * 128, cnt, &err);
+		if (rc != NRC_OK)
+			return fail(rc, err);
+		NRC_CUDA_TRY(launch_infer(p, tm_w, tm_in, m_sms, stream), sink);
+		NRC_CUDA_TRY(cudaEventRecord(m_ev_done[c], stream), sink);
+		NRC_CUDA_TRY(cudaStreamWaitEvent(m_stream_out, m_ev_done[c], 0), sink);
+		NRC_CUDA_TRY(cudaMemcpyAsync((uint8_t *)h_outputs + first * 6, (const uint8_t *)m_stage_out + first * 6, cnt * 6, cudaMemcpyDeviceToHost, m_stream_out), sink);
+		first = end;
+	}
+	NRC_CUDA_TRY(cudaEventRecord(m_ev_out, m_stream_out), sink);
+	NRC_CUDA_TRY(cudaStreamWaitEvent(stream, m_ev_out, 0), sink); // `stream` completes when the last outputs are on the host
 	return NRC_OK;
 }
 
@@ -446,6 +508,14 @@ int nrc_infer_encoded(nrc_handle_t h, const void *d_inputs, void *d_out, uint64_
 	InferParams p{};
 	p.n = n, p.in_mode = NRC_IN_ENCODED, p.out_mode = NRC_OUT_F16VEC3, p.clamp_output = clamp_output, p.out = d_out;
 	return h->state.Infer(p, d_inputs, h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
+}
+
+int nrc_infer_encoded_host(nrc_handle_t h, const void *h_inputs, void *h_outputs, uint64_t n, int clamp_output, void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	if (n == 0)
+		return NRC_OK;
+	NRC_REQUIRE(h_inputs && h_outputs, "nrc_infer_encoded_host: null buffer");
+	return h->state.InferEncodedHost(h_inputs, h_outputs, n, clamp_output, h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
 }
 
 int nrc_infer_unpacked(nrc_handle_t h, const void *d_records, uint32_t stride_bytes, const uint32_t *d_count, uint64_t max_count,

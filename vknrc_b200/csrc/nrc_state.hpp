@@ -66,6 +66,10 @@ public:
 
 	// ---- hot path
 	int Infer(InferParams p, const void *encoded_inputs, const __half *weights, cudaStream_t stream);
+	// The reference harness' whole sequence for one batch of pre-encoded queries - inputs host -> device, launch, outputs
+	// device -> host (test/main.cpp:103-128) - as ONE call on host buffers: the queries are cut in chunks and the three
+	// stages run on three streams (both copy engines + the SMs busy at once), ordered after / before `stream`.
+	int InferEncodedHost(const void *h_inputs, void *h_outputs, uint64_t n, int clamp_output, const __half *weights, cudaStream_t stream);
 	// One cooperative launch of nrc_train_kernel: tp.batch[0..num_batches) (inputs / targets / counts / loss), tp.adam_mode,
 	// tp.accumulate / limit / batch_cap and tp.gradients are the caller's; partials, barrier words and the optimizer
 	// buffers are filled in here. `weights` is the fp16 buffer the forward / backward passes read.
@@ -100,6 +104,13 @@ private:
 	float *m_gradients{nullptr}, *m_partials{nullptr};
 	uint32_t *m_sync_words{nullptr}; // [0] optimizer "last CTA" counter, [2..4] grid barrier {count even, count odd, generation}
 	float *m_prediction_capture{nullptr};
+
+	// host-buffer path: device staging (grown on demand), copy-in / copy-out streams, per-chunk events
+	static constexpr int kHostChunks = 8;
+	void *m_stage_in{nullptr}, *m_stage_out{nullptr};
+	uint64_t m_stage_capacity{0};
+	cudaStream_t m_stream_in{nullptr}, m_stream_out{nullptr};
+	cudaEvent_t m_ev_start{nullptr}, m_ev_in[kHostChunks]{}, m_ev_done[kHostChunks]{}, m_ev_out{nullptr};
 
 	uint64_t *m_comm_local{nullptr};
 	uint64_t *m_comm_inbox[NRC_MAX_RANKS]{};
