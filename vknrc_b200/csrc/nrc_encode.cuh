@@ -2,20 +2,24 @@
 // registers that become the first layer's A operand.
 //   NRCInputEncode        shader/src/NRCRecord.glsl:47-95
 //   one-blob-32 (image)   test/mlp_learning_an_image/gradient.comp:26-44
-// The quartic kernel is written with explicit round-to-nearest intrinsics so that nvcc cannot contract it into FMAs:
-// every fp32 step then rounds exactly where the GLSL source (and oracle/nrc_oracle.c) rounds.
+// Arithmetic contract (tests/test_gpu_parity.py::test_fused_encoding_*):
+//   * frequency features: BIT-EXACT against the unfused fp32 evaluation of the GLSL source (oracle/nrc_oracle.c); the
+//     rewrite below only uses steps that are exact in fp32 (see tri()).
+//   * one-blob features: the quartic kernel is evaluated in Horner form with FMAs (GLSL leaves contraction to the
+//     compiler - the source carries no `precise` - so the reference's own last bit is not defined); the result is within
+//     2 fp32 ulps of the unfused evaluation, i.e. at most one fp16 ulp (or 2.4e-7 near zero) on the encoded feature.
 #pragma once
 #include "sm100_ptx.cuh"
 
 namespace nrc {
 
-__device__ __forceinline__ float quartic_cdf(float x, float inv_radius) { // NRCRecord.glsl:51-56
-	const float u = __fmul_rn(x, inv_radius);
-	const float u2 = __fmul_rn(u, u);
-	const float u4 = __fmul_rn(u2, u2);
-	const float poly = __fadd_rn(__fsub_rn(1.0f, __fmul_rn(2.0f / 3.0f, u2)), __fmul_rn(1.0f / 5.0f, u4));
-	const float v = __fadd_rn(__fmul_rn(__fmul_rn(15.0f / 16.0f, u), poly), 0.5f);
-	return fminf(fmaxf(v, 0.0f), 1.0f);
+// _quartic_cdf(e - x, inv_radius) (NRCRecord.glsl:51-56) for a power-of-two inv_radius: u = fl(fl(e - x) * inv_radius)
+// == fl(e * inv_radius - x * inv_radius) (scaling by a power of two commutes with rounding) = one FMA; 6 instructions.
+__device__ __forceinline__ float quartic_cdf_edge(float x, float edge, float inv_radius) {
+	const float u = fmaf(x, -inv_radius, edge * inv_radius);
+	const float u2 = u * u;
+	const float poly = fmaf(u2, fmaf(u2, 1.0f / 5.0f, -2.0f / 3.0f), 1.0f);
+	return __saturatef(fmaf(u * poly, 15.0f / 16.0f, 0.5f));
 }
 
 // NRCOneBlob4Encode (NRCRecord.glsl:58-63). Bin i is cdf(r_i - x) - cdf(l_i - x) with r_i == l_{i+1}, so the five
@@ -24,17 +28,20 @@ __device__ __forceinline__ void oneblob4(float x, float out[4]) {
 	float c[5];
 #pragma unroll
 	for (int i = 0; i < 5; ++i)
-		c[i] = quartic_cdf(__fsub_rn(0.25f * (float)i, x), 4.0f);
+		c[i] = quartic_cdf_edge(x, 0.25f * (float)i, 4.0f);
 #pragma unroll
 	for (int i = 0; i < 4; ++i)
-		out[i] = __fsub_rn(c[i + 1], c[i]);
+		out[i] = c[i + 1] - c[i];
 }
 
-// _nrc_tri (NRCRecord.glsl:65-68): 2|mod(x - 1/2, 2) - 1| - 1. Every step except (x - 1/2) is exact in fp32.
-__device__ __forceinline__ float tri(float x) {
-	const float a = x - 0.5f;
-	const float m = a - 2.0f * floorf(a * 0.5f);
-	return 2.0f * fabsf(m - 1.0f) - 1.0f;
+// _nrc_tri (NRCRecord.glsl:65-68) of x = scale * p (scale a power of two): 2|mod(x - 1/2, 2) - 1| - 1, in 5 instructions,
+// bit-identical to the step-by-step evaluation:  a = fl(x - 1/2) is the only rounding of the source. h = a / 2 =
+// fl(scale/2 * p - 1/4) (same rounding, scaled); mod(a, 2) = 2 (h - floor h) with h - floor(h) exact; the source's
+// fl(m - 1) equals fl(4 frac - 2) / 2 (again a scaled rounding) and 2|.| - 1 is exact.
+__device__ __forceinline__ float tri_scaled(float p, float scale) {
+	const float h = fmaf(p, 0.5f * scale, -0.25f);
+	const float frac = h - floorf(h);
+	return fabsf(fmaf(frac, 4.0f, -2.0f)) - 1.0f;
 }
 
 // 14 floats (UnpackedNRCInput order) -> 64 features as 32 packed fp16 pairs, slot order NRCRecord.glsl:86-94.
@@ -44,7 +51,7 @@ __device__ __forceinline__ void encode_nrc(const float in[14], uint32_t o[32]) {
 	for (int a = 0; a < 3; ++a)
 #pragma unroll
 		for (int k = 0; k < 12; ++k)
-			f[12 * a + k] = tri((float)(1 << k) * in[a]);
+			f[12 * a + k] = tri_scaled(in[a], (float)(1 << k));
 	oneblob4(in[3], f + 36);
 	oneblob4(in[4], f + 40);
 	oneblob4(in[5], f + 44);
@@ -66,14 +73,14 @@ __device__ __forceinline__ void encode_nrc_half(const float in[14], uint32_t hal
 	if (half == 0) {
 #pragma unroll
 		for (int k = 0; k < 12; ++k)
-			f[k] = tri((float)(1 << k) * in[0]), f[12 + k] = tri((float)(1 << k) * in[1]);
+			f[k] = tri_scaled(in[0], (float)(1 << k)), f[12 + k] = tri_scaled(in[1], (float)(1 << k));
 #pragma unroll
 		for (int k = 0; k < 8; ++k)
-			f[24 + k] = tri((float)(1 << k) * in[2]);
+			f[24 + k] = tri_scaled(in[2], (float)(1 << k));
 	} else {
 #pragma unroll
 		for (int k = 8; k < 12; ++k)
-			f[k - 8] = tri((float)(1 << k) * in[2]);
+			f[k - 8] = tri_scaled(in[2], (float)(1 << k));
 		oneblob4(in[3], f + 4);
 		oneblob4(in[4], f + 8);
 		oneblob4(in[5], f + 12);
@@ -94,8 +101,8 @@ __device__ __forceinline__ void encode_oneblob32_half(float x, uint32_t o[16]) {
 #pragma unroll
 	for (int i = 0; i < 16; ++i) {
 		const float l0 = (float)(2 * i) / 32.0f, r0 = (float)(2 * i + 1) / 32.0f, r1 = (float)(2 * i + 2) / 32.0f;
-		const float e0 = __fsub_rn(quartic_cdf(__fsub_rn(r0, x), 32.0f), quartic_cdf(__fsub_rn(l0, x), 4.0f));
-		const float e1 = __fsub_rn(quartic_cdf(__fsub_rn(r1, x), 32.0f), quartic_cdf(__fsub_rn(r0, x), 4.0f));
+		const float e0 = quartic_cdf_edge(x, r0, 32.0f) - quartic_cdf_edge(x, l0, 4.0f);
+		const float e1 = quartic_cdf_edge(x, r1, 32.0f) - quartic_cdf_edge(x, r0, 4.0f);
 		o[i] = sm100::cvt_pack_f16x2(e0, e1);
 	}
 }
@@ -108,8 +115,8 @@ __device__ __forceinline__ void encode_oneblob32(float u, float v, uint32_t o[32
 #pragma unroll
 		for (int i = 0; i < 16; ++i) {
 			const float l0 = (float)(2 * i) / 32.0f, r0 = (float)(2 * i + 1) / 32.0f, r1 = (float)(2 * i + 2) / 32.0f;
-			const float e0 = __fsub_rn(quartic_cdf(__fsub_rn(r0, x), 32.0f), quartic_cdf(__fsub_rn(l0, x), 4.0f));
-			const float e1 = __fsub_rn(quartic_cdf(__fsub_rn(r1, x), 32.0f), quartic_cdf(__fsub_rn(r0, x), 4.0f));
+			const float e0 = quartic_cdf_edge(x, r0, 32.0f) - quartic_cdf_edge(x, l0, 4.0f);
+			const float e1 = quartic_cdf_edge(x, r1, 32.0f) - quartic_cdf_edge(x, r0, 4.0f);
 			o[16 * h + i] = sm100::cvt_pack_f16x2(e0, e1);
 		}
 	}

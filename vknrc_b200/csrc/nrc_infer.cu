@@ -68,8 +68,28 @@ __device__ __forceinline__ uint32_t pack_rgba8(float r, float g, float b) { // i
 	return q(r) | (q(g) << 8) | (q(b) << 16) | (255u << 24);
 }
 
+// Screen-destined results composite into two images read-modify-write (nrc_inference.comp:53-59). The slot threads fetch
+// the dst word and then the pixel's bias / factor a few layers ahead of the write (ScatterPrefetch), so that neither
+// dependent load level sits in front of the slot's next MMA.
+struct ScatterPrefetch {
+	uint32_t dst;
+	float4 bf;
+	float2 gb;
+};
+__device__ __forceinline__ void prefetch_dst(const InferParams &p, uint64_t gi, bool valid, ScatterPrefetch &pf) {
+	pf.dst = valid ? __ldg(p.dst + gi * p.dst_stride_u32) : NRC_EVAL_INVALID_DST;
+}
+__device__ __forceinline__ void prefetch_pixel(const InferParams &p, ScatterPrefetch &pf) {
+	if (pf.dst != NRC_EVAL_INVALID_DST && (pf.dst & 1u) == 0u) {
+		const uint32_t e = pf.dst >> 1, x = e & 0x7FFFu, y = e >> 15;
+		const uint64_t at = (uint64_t)y * p.image_pitch + x;
+		pf.bf = *((const float4 *)p.bias_factor_r + at);
+		pf.gb = ((const float2 *)p.factor_gb)[at];
+	}
+}
+
 // nrc_inference.comp:48-73
-__device__ __forceinline__ void write_result(const InferParams &p, uint64_t gi, float y0, float y1, float y2) {
+__device__ __forceinline__ void write_result(const InferParams &p, uint64_t gi, float y0, float y1, float y2, const ScatterPrefetch &pf) {
 	if (p.out_mode == NRC_OUT_F16VEC3) {
 		if (p.clamp_output)
 			y0 = fmaxf(y0, 0.0f), y1 = fmaxf(y1, 0.0f), y2 = fmaxf(y2, 0.0f);
@@ -79,15 +99,14 @@ __device__ __forceinline__ void write_result(const InferParams &p, uint64_t gi, 
 		((uint32_t *)p.out)[gi] = pack_rgba8(y0, y1, y2);
 	} else { // NRC_OUT_SCATTER
 		y0 = fmaxf(y0, 0.0f), y1 = fmaxf(y1, 0.0f), y2 = fmaxf(y2, 0.0f);
-		const uint32_t dst = p.dst[gi * p.dst_stride_u32];
+		const uint32_t dst = pf.dst;
 		if (dst == NRC_EVAL_INVALID_DST)
 			return;
 		if ((dst & 1u) == 0u) {
 			const uint32_t e = dst >> 1, x = e & 0x7FFFu, y = e >> 15;
 			float4 *bf = (float4 *)p.bias_factor_r + (uint64_t)y * p.image_pitch + x;
-			const float2 gb = ((const float2 *)p.factor_gb)[(uint64_t)y * p.image_pitch + x];
-			float4 v = *bf;
-			*bf = make_float4(v.x + v.w * y0, v.y + gb.x * y1, v.z + gb.y * y2, 0.0f);
+			const float4 v = pf.bf;
+			*bf = make_float4(v.x + v.w * y0, v.y + pf.gb.x * y1, v.z + pf.gb.y * y2, 0.0f);
 		} else {
 			const uint32_t e = dst >> 1, b = e & 3u, l = (e >> 2) & 0x3FFFu, r = e >> 16;
 			NrcTrainRecord *recs = (NrcTrainRecord *)p.train_records[b];
@@ -279,6 +298,7 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 	float pend_y0 = 0.0f, pend_y1 = 0.0f, pend_y2 = 0.0f;
 	uint64_t pend_gi = 0;
 	bool pend = false;
+	ScatterPrefetch pf{};
 	for (uint32_t it = 0; it < slot_tiles; ++it) {
 		const uint32_t j = s + it * NT;
 		const uint32_t tile = blockIdx.x + j * gridDim.x;
@@ -324,8 +344,14 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 				__syncwarp();
 			}
 			if (l == NRC_INFER_FLUSH_LAYER && pend) {
-				write_result(p, pend_gi, pend_y0, pend_y1, pend_y2);
+				write_result(p, pend_gi, pend_y0, pend_y1, pend_y2, pf);
 				pend = false;
+			}
+			if (p.out_mode == NRC_OUT_SCATTER) { // (after the previous tile's flush, which consumed the old prefetch)
+				if (l == 1)
+					prefetch_dst(p, gi, valid, pf);
+				if (l == 3)
+					prefetch_pixel(p, pf);
 			}
 			// ---- epilogue of layer l
 			NRC_TRACE_EV(s, NRC_TRACE_TAG(2));
@@ -355,7 +381,7 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 				pend_y0 = __half2float(__ushort_as_half((unsigned short)y[0])), pend_y1 = __half2float(__ushort_as_half((unsigned short)y[1]));
 				pend_y2 = __half2float(__ushort_as_half((unsigned short)y[2]));
 				if (NRC_INFER_FLUSH_LAYER < 0 && pend) {
-					write_result(p, pend_gi, pend_y0, pend_y1, pend_y2);
+					write_result(p, pend_gi, pend_y0, pend_y1, pend_y2, pf);
 					pend = false;
 				}
 			}
@@ -398,7 +424,7 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 				pend = valid, pend_gi = gi;
 				pend_y0 = __uint_as_float(y[0]), pend_y1 = __uint_as_float(y[1]), pend_y2 = __uint_as_float(y[2]);
 				if (NRC_INFER_FLUSH_LAYER < 0 && pend) {
-					write_result(p, pend_gi, pend_y0, pend_y1, pend_y2);
+					write_result(p, pend_gi, pend_y0, pend_y1, pend_y2, pf);
 					pend = false;
 				}
 			}
@@ -406,7 +432,7 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 		}
 	}
 	if (pend)
-		write_result(p, pend_gi, pend_y0, pend_y1, pend_y2);
+		write_result(p, pend_gi, pend_y0, pend_y1, pend_y2, pf);
 #ifdef NRC_TRACE
 	if (blockIdx.x == 0 && (threadIdx.x & 127) == 0 && (threadIdx.x >> 7) < 4) {
 		for (uint32_t i = 0; i < trace_n; ++i)
