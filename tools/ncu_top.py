@@ -4,7 +4,9 @@ rep = sys.argv[1]; topn = int(sys.argv[2]) if len(sys.argv) > 2 else 25
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
-want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
+want = ["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.sum", "sm__ops_path_tensor_op_utchmma_src_fp16_dst_fp32_sparsity_off.avg.pct_of_peak_sustained_elapsed",
+        "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.avg.per_second",
         "sm__pipe_tensor_subpipe_hmma_cycles_active_realtime.avg", "sm__pipe_tensor_cycles_active_realtime.avg.pct_of_peak_sustained_elapsed",
         "sm__inst_executed_pipe_tensor_subpipe_hmma.sum", "launch__registers_per_thread", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
@@ -12,7 +14,7 @@ want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
 for r in rows[2:]:
     print("==", r[hdr.index("Kernel Name")][:100])
     for h, u, v in zip(hdr, units, r):
-        if any(h.endswith(w) or h == w for w in want):
+        if any(h == w or h.endswith("." + w) for w in want):
             print(f"   {h:90s} {v} {u}")
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
