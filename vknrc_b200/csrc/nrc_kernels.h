@@ -112,7 +112,8 @@ struct TrainParams {
 	uint32_t limit;        // number of leading elements to produce (20672 for a caller's dW, NRC_GRAD_STRIDE otherwise)
 	uint32_t batch_cap;    // d_count is clamped in place to this (nrc_train_prepare.comp:17-19)
 	AdamParams adam;       // use_weights / use_ema are taken from here when adam_mode == 2
-	uint32_t *grid_bar;    // {arrival count (even gen), arrival count (odd gen), generation}: zero-initialised, owned by the state
+	uint32_t *grid_bar;    // monotonic arrival counter of the grid barrier (owned by the state, never reset)
+	uint32_t grid_bar_base; // its value before this launch (every launch adds grid * (2 * num_batches - 1))
 	CommParams comm;
 };
 
@@ -125,7 +126,7 @@ struct SgdParams { // mlp_learning_an_image/optimize.comp:21-29
 
 cudaError_t launch_infer(const InferParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream);
 // cooperative launch: grid = min(#tiles of the largest batch, #SMs) CTAs, all co-resident
-cudaError_t launch_train(const TrainParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream);
+cudaError_t launch_train(const TrainParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream, uint32_t *grid_out = nullptr);
 cudaError_t launch_unpack(const void *packed, uint32_t stride_bytes, uint64_t n, const NrcScene &scene, float *out14, cudaStream_t stream);
 cudaError_t launch_adam(const AdamParams &p, cudaStream_t stream);
 cudaError_t launch_sgd(const SgdParams &p, cudaStream_t stream);

@@ -209,6 +209,7 @@ int NrcState::upload_initial(const float *w) {
 	NRC_CUDA_TRY(cudaMemcpy(m_optimizer_entries, e.data(), e.size() * sizeof(NrcOptimizerEntry), cudaMemcpyHostToDevice), sink);
 	NRC_CUDA_TRY(cudaMemcpy(m_optimizer_state, &st, sizeof(st), cudaMemcpyHostToDevice), sink);
 	NRC_CUDA_TRY(cudaMemset(m_sync_words, 0, 8 * sizeof(uint32_t)), sink);
+	m_grid_bar_count = 0;
 	return NRC_OK;
 }
 
@@ -318,7 +319,7 @@ int NrcState::Train(TrainParams tp, const void *encoded_inputs, const __half *we
 	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
 	for (uint32_t b = 0; b < tp.num_batches; ++b)
 		tp.batch[b].partials = m_partials;
-	tp.grid_bar = m_sync_words + 2;
+	tp.grid_bar = m_sync_words + 2, tp.grid_bar_base = m_grid_bar_count;
 	tp.adam.gradients = tp.gradients, tp.adam.entries = m_optimizer_entries, tp.adam.opt_state = m_optimizer_state;
 	tp.adam.done_counter = m_sync_words, tp.adam.weights = m_weights, tp.adam.use_weights = m_use_weights;
 	tp.adam.use_ema = m_use_ema_weights ? 1 : 0;
@@ -329,7 +330,9 @@ int NrcState::Train(TrainParams tp, const void *encoded_inputs, const __half *we
 			tp.comm.inbox[r] = m_comm_inbox[r];
 		m_comm_epoch += tp.num_batches;
 	}
-	NRC_CUDA_TRY(launch_train(tp, tm_w, tm_in, m_sms, stream), sink);
+	uint32_t grid = 0;
+	NRC_CUDA_TRY(launch_train(tp, tm_w, tm_in, m_sms, stream, &grid), sink);
+	m_grid_bar_count += grid * (2u * tp.num_batches - 1u); // what the launch adds to the grid-barrier counter
 	return NRC_OK;
 }
 

@@ -102,7 +102,8 @@ private:
 	NrcOptimizerState *m_optimizer_state{nullptr};
 	NrcOptimizerEntry *m_optimizer_entries{nullptr};
 	float *m_gradients{nullptr}, *m_partials{nullptr};
-	uint32_t *m_sync_words{nullptr}; // [0] optimizer "last CTA" counter, [2..4] grid barrier {count even, count odd, generation}
+	uint32_t *m_sync_words{nullptr}; // [0] optimizer "last CTA" counter, [2] grid-barrier arrival counter (monotonic)
+	uint32_t m_grid_bar_count{0};    // host mirror of [2]: what it will read once every launch enqueued so far has run
 	float *m_prediction_capture{nullptr};
 
 	// host-buffer path: device staging (grown on demand), copy-in / copy-out streams, per-chunk events

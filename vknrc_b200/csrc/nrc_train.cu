@@ -118,33 +118,33 @@ __device__ __forceinline__ void publish_state_if_last(const AdamParams &a, const
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Grid barrier. All CTAs of the (cooperative) launch are co-resident. bar[0] = arrival count, bar[1] = generation.
-// Writers' global stores become visible to every later reader, including TMA (async proxy) reads of updated weights.
+// Grid barrier. All CTAs of the (cooperative) launch are co-resident. ONE monotonically increasing arrival counter,
+// never reset: barrier k of a launch is passed when the counter reaches base + (k + 1) * gridDim.x, where `base` is the
+// counter's value before the launch (tracked by the host object: every launch adds gridDim.x * #barriers; wrap-around
+// is harmless, the comparison is on the signed difference). An arrival is one fire-and-forget red; the waiters poll the
+// counter itself, so a barrier costs fence + one-way red + one load round trip (1800 cycles; the earlier generation-word
+// scheme - load generation, atomic with return, last arriver stores, the others poll - measured 3050).
+// Release: the CTA barrier orders every thread's global writes before thread 0's __threadfence + arrival. Acquire:
+// readers after the barrier use L2 loads (ld.cg / TMA / volatile), so no trailing fence. kProxyFence: the writes before
+// the barrier are read through the async proxy (TMA) after it.
 // ------------------------------------------------------------------------------------------------------------------
-// ------------------------------------------------------------------------------------------------------------------
-// Grid barrier. All CTAs of the (cooperative) launch are co-resident. bar[0], bar[1] = arrival counters used by even /
-// odd generations, bar[2] = generation. Release: the CTA barrier orders every thread's global writes before thread 0's
-// __threadfence + arrival. Acquire: readers after the barrier use L2 loads (ld.cg / TMA / volatile), so no trailing fence.
-// The last arriver resets its counter with a plain store: that counter is next used two generations later, i.e. after
-// this CTA's own next arrival fence. kProxyFence: the writes before the barrier (the new weights) are read through the
-// async proxy (TMA) after it.
-// ------------------------------------------------------------------------------------------------------------------
-template <bool kProxyFence> __device__ __forceinline__ void grid_sync(uint32_t *bar) {
+#ifndef NRC_GRID_SYNC_BACKOFF
+#define NRC_GRID_SYNC_BACKOFF 50
+#endif
+template <bool kProxyFence> __device__ __forceinline__ void grid_sync(uint32_t *counter, uint32_t &target) {
 	if (kProxyFence)
 		asm volatile("fence.proxy.async;" ::: "memory");
 	__syncthreads();
 	if (threadIdx.x == 0) {
-		uint32_t my_gen, seen;
-		asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(my_gen) : "l"(bar + 2) : "memory"); // cannot advance before this CTA arrives
+		target += gridDim.x;
 		__threadfence();
-		uint32_t *count = bar + (my_gen & 1u);
-		if (atomicAdd(count, 1u) == gridDim.x - 1) {
-			*count = 0;
-			asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(bar + 2), "r"(my_gen + 1) : "memory");
-		} else {
-			do {
-				asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(bar + 2) : "memory");
-			} while (seen == my_gen);
+		asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+		uint32_t seen;
+		for (;;) {
+			asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+			if ((int32_t)(seen - target) >= 0)
+				break;
+			__nanosleep(NRC_GRID_SYNC_BACKOFF); // 148 pollers on one L2 line slow the arrivals down: 2440 -> 2320 cycles
 		}
 	}
 	__syncthreads();
@@ -304,6 +304,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		arrive_a_ready();
 	}
 	uint32_t w_reloads = 0; // weight re-stagings by the epilogue warps so far (w_ready phase)
+	uint32_t bar_target = tp.grid_bar_base; // (meaningful in thread 0 only)
 
 #pragma unroll 1
 	for (uint32_t b = 0; b < tp.num_batches; ++b) {
@@ -618,7 +619,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		// ============================================================ deterministic reduction (+ optimizer step)
 		NrcOptimizerState pending_state{};
 		bool publish_pending = false;
-		grid_sync<false>(tp.grid_bar);
+		grid_sync<false>(tp.grid_bar, bar_target);
 		NRC_GTRACE(9);
 		{
 			const uint32_t num_partials = gridDim.x;
@@ -758,7 +759,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		}
 		NRC_GTRACE(0x54);
 		if (b + 1 < tp.num_batches) {
-			grid_sync<false>(tp.grid_bar); // the next batch runs on the weights (and optimizer state) just written
+			grid_sync<false>(tp.grid_bar, bar_target); // the next batch runs on the weights (and optimizer state) just written
 			if (publish_pending && blockIdx.x == 0 && threadIdx.x == 0)
 				*tp.adam.opt_state = pending_state; // read again only after the next batch's first grid barrier
 		}
@@ -799,13 +800,15 @@ static cudaError_t launch_train_t(const TrainParams &p, const CUtensorMap &tm_w,
 	return cudaLaunchKernelEx(&cfg, kern, p, tm_w, tm_in);
 }
 
-cudaError_t launch_train(const TrainParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream) {
+cudaError_t launch_train(const TrainParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream, uint32_t *grid_out) {
 	uint64_t ntiles = 1; // an empty batch still runs one CTA: it emits an all-zero partial and runs the reduction
 	for (uint32_t b = 0; b < p.num_batches; ++b) {
 		const uint64_t t = (p.batch[b].n + NRC_TILE - 1) / NRC_TILE;
 		ntiles = t > ntiles ? t : ntiles;
 	}
 	const uint32_t grid = (uint32_t)(ntiles < (uint64_t)sms ? ntiles : (uint64_t)sms);
+	if (grid_out)
+		*grid_out = grid;
 	switch (p.batch[0].in_mode) {
 	case NRC_IN_ENCODED:
 		return launch_train_t<NRC_IN_ENCODED>(p, tm_w, tm_in, grid, stream);
