@@ -93,6 +93,30 @@ def test_gradient_encoded_matches_oracle(nrc, oracle_mod, n):
     assert max(layer_rel_err(f32(dw), ref16)) <= 5e-2
 
 
+def test_multi_tile_encoded_gradient_pipeline(nrc, oracle_mod):
+    """Sizes at which every CTA runs several tiles: the forward pass of tile r overlaps the backward pass of tile r - 1
+    (two tiles in flight, rotating activation buffers, TMA input tiles landing in recycled buffers). The batch gradient is
+    additive over any split of the records, so the one-launch result must equal the sum over single-tile-per-CTA chunks
+    (each of those paths is checked against the oracle above) up to fp32 reassociation; it must be bit-reproducible; and a
+    ragged size that leaves some CTAs one tile short must agree too."""
+    g = torch.Generator(device="cuda").manual_seed(77)
+    w = dev(he_weights(55).astype(np.float16))
+    for n in (148 * 128 * 3, 148 * 128 * 5 + 128 * 37 + 19, 1 << 18):
+        x = torch.rand((n, 64), device="cuda", generator=g).half()
+        t = torch.rand((n, 3), device="cuda", generator=g).half()
+        dw = torch.zeros(nrc.WEIGHT_COUNT, dtype=torch.float32, device="cuda")
+        nrc.mlp_gradient_encoded(w, dw, x, t)
+        again = torch.zeros_like(dw)
+        nrc.mlp_gradient_encoded(w, again, x, t)
+        assert torch.equal(dw, again), "batch reduction must be bit-reproducible run to run"
+        parts = torch.zeros(nrc.WEIGHT_COUNT, dtype=torch.float64, device="cuda")
+        for lo in range(0, n, 16384):
+            d = torch.zeros(nrc.WEIGHT_COUNT, dtype=torch.float32, device="cuda")
+            nrc.mlp_gradient_encoded(w, d, x[lo:lo + 16384].contiguous(), t[lo:lo + 16384].contiguous())
+            parts += d.double()
+        assert max(layer_rel_err(f32(dw), parts.cpu().numpy())) <= 1e-4
+
+
 def test_gradient_encoded_accumulates_and_is_deterministic(nrc, golden):
     w, x, t = dev(golden["weights_he_fp32"].astype(np.float16)), dev(golden["inputs"]), dev(golden["targets"])
     dw = torch.zeros(nrc.WEIGHT_COUNT, dtype=torch.float32, device="cuda")

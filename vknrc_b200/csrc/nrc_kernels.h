@@ -115,6 +115,7 @@ struct TrainParams {
 	uint32_t *grid_bar;    // monotonic arrival counter of the grid barrier (owned by the state, never reset)
 	uint32_t grid_bar_base; // its value before this launch (every launch adds grid * (2 * num_batches - 1))
 	CommParams comm;
+	uint32_t pool_tiles;   // activation tiles in shared memory (set by launch_train: 8, or 6 when no CTA has a second tile)
 };
 
 struct SgdParams { // mlp_learning_an_image/optimize.comp:21-29

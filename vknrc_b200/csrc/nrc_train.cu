@@ -26,6 +26,7 @@
 #include "nrc_kernels.h"
 #include "nrc_encode.cuh"
 #include "nrc_unpack.cuh"
+#include <type_traits>
 
 using namespace sm100;
 
@@ -39,6 +40,8 @@ __device__ unsigned int g_nrc_gtrace_n;
 		if (blockIdx.x == 0 && threadIdx.x == 0 && gtrace_n < NRC_GTRACE_CAP)                                          \
 			gtrace[gtrace_n++] = make_uint2((uint32_t)(tag), (uint32_t)clock64());                                     \
 	} while (0)
+#elif defined(NRC_GTRACE_FENCE) // experiment: the trace points as pure compiler scheduling fences
+#define NRC_GTRACE(tag) asm volatile("" ::: "memory")
 #else
 #define NRC_GTRACE(tag)
 #endif
@@ -47,15 +50,17 @@ namespace nrc {
 
 namespace {
 constexpr uint32_t kWOff = 0;                         // 6 x 8 KB weights
-constexpr uint32_t kActOff = NRC_LAYERS * 8192;       // 6 x 16 KB activations a_0..a_5 (reused as fp32 staging of the partial)
-constexpr uint32_t kDeltaOff = kActOff + 6 * 16384;   // 2 x 16 KB deltas (ping-pong)
-constexpr uint32_t kBarOff = kDeltaOff + 2 * 16384;
-constexpr uint32_t kTrainSmemBytes = kBarOff + 256 + 1024;
-constexpr uint32_t kColDW5 = 320, kColWork = 384;     // TMEM columns: dW_l at 64*l, dW_5^T at 320, working D at 384
+constexpr uint32_t kPoolOff = NRC_LAYERS * 8192;      // P x 16 KB activation tiles (also fp32 staging of the partial): P = 8 when a CTA
+                                                      // runs several tiles (two in flight), 6 when every CTA has at most one - the smaller
+                                                      // footprint leaves the L1 32 KB more, which the latency-bound frame feels (-2 us)
+// then 2 x 16 KB deltas (ping-pong: delta_l lives in buffer (5 - l) & 1), then the barriers
+constexpr uint32_t train_smem_bytes(uint32_t pool_tiles) { return kPoolOff + (pool_tiles + 2) * 16384 + 256 + 1024; }
+constexpr uint32_t kColDW5 = 320;                     // TMEM columns: dW_l at 64*l, dW_5^T at 320,
+constexpr uint32_t kColWorkF = 384, kColWorkB = 448;  // working accumulators of the forward / backward stream
 constexpr uint32_t kEpiWarps = 8, kEpiThreads = 256, kIssueWarp = 8;
 constexpr int kTrainThreads = 288;
 constexpr uint32_t kReduceBlocks = NRC_GRAD_STRIDE / 64; // the reduction works on blocks of 64 consecutive floats
-static_assert(NRC_GRAD_STRIDE % 64 == 0 && NRC_GRAD_STRIDE * 4 <= 6 * 16384, "partial staging must fit the activation region");
+static_assert(NRC_GRAD_STRIDE % 64 == 0, "the reduction works on 64-float blocks");
 } // namespace
 
 // bilinear RGBA8 fetch, clamp-to-edge, normalised coordinates (the sampler of mlp_learning_an_image/main.cpp:121-124)
@@ -185,10 +190,11 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	__shared__ float scratch[16];
 	__shared__ uint32_t peer_counts[NRC_MAX_RANKS];
 	uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-	uint8_t *w_sm = smem + kWOff, *act_sm = smem + kActOff, *delta_sm = smem + kDeltaOff;
-	uint64_t *bars = (uint64_t *)(smem + kBarOff);
-	uint64_t *w_full = bars, *in_full = bars + 1, *d_full = bars + 2, *tile_done = bars + 3, *a_ready = bars + 4, *w_ready = bars + 5;
-	uint32_t *tmem_slot = (uint32_t *)(bars + 6);
+	uint8_t *w_sm = smem + kWOff, *pool_sm = smem + kPoolOff, *delta_sm = pool_sm + tp.pool_tiles * 16384;
+	uint64_t *bars = (uint64_t *)(delta_sm + 2 * 16384);
+	uint64_t *w_full = bars, *in_full = bars + 1, *df_full = bars + 2, *db_full = bars + 3, *dw1_done = bars + 4, *tile_done = bars + 5;
+	uint64_t *af_ready = bars + 6, *ab_ready = bars + 7, *d5_ready = bars + 8, *w_ready = bars + 9;
+	uint32_t *tmem_slot = (uint32_t *)(bars + 10);
 #ifdef NRC_TRACE
 	__shared__ uint2 gtrace[NRC_GTRACE_CAP];
 	uint32_t gtrace_n = 0;
@@ -201,8 +207,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	const uint32_t row = q * 32 + lane;
 
 	if (threadIdx.x == 0) {
-		mbar_init(w_full, 1), mbar_init(in_full, 1), mbar_init(d_full, 1), mbar_init(tile_done, 1), mbar_init(a_ready, kEpiWarps);
-		mbar_init(w_ready, kEpiWarps);
+		mbar_init(w_full, 1), mbar_init(in_full, 1), mbar_init(df_full, 1), mbar_init(db_full, 1), mbar_init(dw1_done, 1), mbar_init(tile_done, 1);
+		mbar_init(af_ready, kEpiWarps), mbar_init(ab_ready, kEpiWarps), mbar_init(d5_ready, kEpiWarps), mbar_init(w_ready, kEpiWarps);
 		fence_mbar_init();
 	}
 	if (warp == kIssueWarp)
@@ -220,18 +226,18 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	constexpr uint32_t id_dw5t = make_idesc_f16_f32(64, 16, true, true);  // dW_5^T: A = a_5 MN-major, B = delta_5 MN-major
 	// UMMA descriptors differ only in the start-address field: desc(addr + off) = desc(addr) + (off >> 4)
 	// (only the start-address field = the low word varies; see mma_ss_lh)
-	const uint32_t w_desc = smem_desc_lo(smem_u32(w_sm)), act_desc = smem_desc_lo(smem_u32(act_sm)), del_desc = smem_desc_lo(smem_u32(delta_sm));
+	const uint32_t w_desc = smem_desc_lo(smem_u32(w_sm)), pool_desc = smem_desc_lo(smem_u32(pool_sm)), del_desc = smem_desc_lo(smem_u32(delta_sm));
 	constexpr uint32_t dhi = kSmemDescHiSw128;
-	const uint32_t d_issue = tmem + kColWork;                           // issuer's view of the working accumulator
-	const uint32_t d_mine = tmem_addr(tmem, q * 32, kColWork + 32 * h); // this thread's 32 columns of its row
+	const uint32_t df_issue = tmem + kColWorkF, db_issue = tmem + kColWorkB; // issuer's view of the two working accumulators
+	const uint32_t df_mine = tmem_addr(tmem, q * 32, kColWorkF + 32 * h), db_mine = tmem_addr(tmem, q * 32, kColWorkB + 32 * h);
 
 	// operand stored (generic-proxy smem writes fenced to the async proxy) + accumulator drained -> one arrival per warp
-	auto arrive_a_ready = [&]() {
+	auto arrive_ready = [&](uint64_t *bar) {
 		fence_proxy_async_smem();
 		tc_fence_before();
 		__syncwarp();
 		if (lane == 0)
-			mbar_arrive(a_ready);
+			mbar_arrive(bar);
 	};
 	auto store_half_row = [&](uint8_t *tile, const uint32_t *o16) { // 16 packed pairs = 32 columns = 4 swizzled 16 B chunks
 		uint8_t *r = tile + row * 128;
@@ -241,7 +247,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	};
 
 	// this thread's half row of a_0 for record `tile * 128 + row` of batch `bp` (n = the batch's clamped record count)
-	auto encode_tile_row = [&](const GradParams &bp, uint64_t n, uint32_t tile) {
+	auto encode_tile_row = [&](const GradParams &bp, uint64_t n, uint32_t tile, uint8_t *dst_tile) {
 		const uint64_t gi = (uint64_t)tile * NRC_TILE + row;
 		const bool valid = gi < n;
 		uint32_t o[16];
@@ -274,7 +280,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			if (valid)
 				encode_oneblob32_half(sc * (float)(h ? py : px), o);
 		}
-		store_half_row(act_sm, o);
+		store_half_row(dst_tile, o);
 	};
 	auto batch_count = [&](const GradParams &bp) -> uint64_t { // nrc_train_prepare.comp:17-18: count = min(count, capacity)
 		uint64_t n = bp.n;
@@ -289,19 +295,25 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		return blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 	};
 
-	// phases / counters that run across tiles and batches
-	uint32_t d_ph = 0;      // epilogue threads: parity of the next d_full completion
-	uint32_t ar_ph = 0;     // issuer: parity of the next a_ready completion
-	uint32_t tile_base = 0; // tiles this CTA processed in earlier batches (tile_done / in_full phase = tile number & 1)
+	// mbarrier phase counters (every barrier completes once per use; the waiter tracks the parity of its next wait).
+	// Hand-offs: af_ready = a_k stored (forward epilogue k-1 or the input encoder) -> forward MMAs k; ab_ready = delta_l
+	// stored by backward epilogue l+1 -> backward MMAs l; d5_ready = delta_5 stored by the forward epilogue of the output
+	// layer -> backward MMAs 5 of the next round (a barrier of its own: nothing orders it against the previous tile's
+	// last ab_ready phase); df_full / db_full = accumulator ready; dw1_done (pre-encoded inputs) = dW_1 has finished
+	// reading a_1, whose buffer the next TMA input tile overwrites.
+	uint32_t df_ph = 0, db_ph = 0;            // epilogue threads
+	uint32_t af_ph = 0, ab_ph = 0, d5_ph = 0; // issuer
+	uint32_t in_ph = 0, dw1_ph = 0;           // issuer: TMA input tiles, dw1_done
+	uint32_t tile_base = 0;                   // tiles of earlier batches of this launch (tile_done completes once per tile)
 
 	// The first tile of a batch is encoded ahead of time: for batch 0 right here (while the weights stream in), for batch
 	// b + 1 at the end of batch b's gradient phase - before the grid barriers, the reduction and the weight reload, none of
-	// which the encoding depends on.
+	// which the encoding depends on. It always goes to pool buffer 0 (the rotation below restarts with every batch).
 	uint64_t n = batch_count(tp.batch[0]);
 	uint32_t my_tiles = tiles_of_this_cta(n);
 	if (IN_MODE != NRC_IN_ENCODED && warp < kEpiWarps && my_tiles) {
-		encode_tile_row(tp.batch[0], n, blockIdx.x);
-		arrive_a_ready();
+		encode_tile_row(tp.batch[0], n, blockIdx.x, pool_sm);
+		arrive_ready(af_ready);
 	}
 	uint32_t w_reloads = 0; // weight re-stagings by the epilogue warps so far (w_ready phase)
 	uint32_t bar_target = tp.grid_bar_base; // (meaningful in thread 0 only)
@@ -342,6 +354,29 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 				mbar_arrive(w_ready);
 		}
 
+		// ---------------------------------------------------------------------------------------------------------------
+		// Gradient phase. The CTA's tiles run as a two-stage software pipeline over "rounds": round r carries the FORWARD
+		// pass of tile r and the BACKWARD pass of tile r - 1, step k = 0..5 of a round pairing forward layer k with backward
+		// layer l = 5 - k. The two streams use different working accumulators, so while the epilogue warps convert one
+		// stream's accumulator the tensor pipe runs the other stream's MMAs.
+		//   forward  step k : D_F = a_k W_k^T               -> a_{k+1} = relu(D_F)   (k = 5: prediction -> loss gradient delta_5)
+		//   backward step l : D_B = delta_l W_l             -> delta_{l-1} = D_B * [a_l > 0]   (two delta buffers, ping-pong)
+		//                     dW_l += delta_l^T a_l          (accumulates in TMEM across all tiles of the CTA)
+		// Activation tiles live in a pool of eight 16 KB buffers: the forward tile holds a_0..a_{k+1}, the backward tile
+		// a_0..a_l, i.e. (k + 2) + (l + 1) = 8 at every step, and a buffer is handed over the moment its last reader is done:
+		//   a_{k+1} of a tile takes the buffer of a_{6-k} of the tile before it (k >= 1; freed by dW_{6-k} one step earlier),
+		//   a_0 / a_1 take the buffers of a_1 / a_0 two tiles back (freed by dW_1 / dW_0 at the end of the previous round).
+		// Every reuse is ordered by a tcgen05.commit that was issued after the last MMA reading the old contents.
+		// ---------------------------------------------------------------------------------------------------------------
+		uint32_t fw[6] = {0, 1, 2, 3, 4, 5}, bw[6] = {7, 6, 0, 0, 0, 0}; // pool buffers of the forward / backward tile's a_0..a_5
+		auto rotate_tiles = [&]() {
+			const uint32_t n0 = bw[1], n1 = bw[0], n2 = fw[5], n3 = fw[4], n4 = fw[3], n5 = fw[2];
+#pragma unroll
+			for (int i = 0; i < 6; ++i)
+				bw[i] = fw[i];
+			fw[0] = n0, fw[1] = n1, fw[2] = n2, fw[3] = n3, fw[4] = n4, fw[5] = n5;
+		};
+
 		if (my_tiles == 0) { // nothing to do: contribute an all-zero partial so the reduction stays shape-stable
 			for (uint32_t i = threadIdx.x; i < NRC_GRAD_STRIDE; i += blockDim.x)
 				my_partial[i] = 0.0f;
@@ -356,66 +391,86 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 				}
 				if (IN_MODE == NRC_IN_ENCODED) {
 					mbar_arrive_expect_tx(in_full, 16384);
-					tma_load_2d(act_sm, &tm_in, 0, (int32_t)(blockIdx.x * NRC_TILE), in_full);
+					tma_load_2d(pool_sm, &tm_in, 0, (int32_t)(blockIdx.x * NRC_TILE), in_full);
 				}
 				if (b == 0)
 					mbar_wait(w_full, 0);
 				else
 					mbar_wait(w_ready, w_reloads & 1);
-#pragma unroll 1
-				for (uint32_t j = 0; j < my_tiles; ++j) {
-					const uint32_t T = tile_base + j;
+				// (three instantiations - forward only / both / backward only - so that the one-tile-per-CTA case of the
+				// paper-sized batch runs straight-line code instead of hopping over the other stream's half of every step)
+				auto issue_round = [&](auto HF, auto HB, uint32_t r) {
+					constexpr bool has_f = decltype(HF)::value, has_b = decltype(HB)::value;
 #pragma unroll
-					for (int l = 0; l < NRC_LAYERS; ++l) { // ---- forward
-						if (IN_MODE == NRC_IN_ENCODED && l == 0) {
-							mbar_wait(in_full, T & 1);
-						} else {
-							mbar_wait(a_ready, ar_ph);
-							ar_ph ^= 1;
+					for (int k = 0; k < NRC_LAYERS; ++k) {
+						const int l = 5 - k;
+						if (has_b && k == 0) { // delta_5 stored - and the forward accumulator of the output layer drained by every warp
+							mbar_wait(d5_ready, d5_ph);
+							d5_ph ^= 1;
 						}
-						tc_fence_after();
-						const uint32_t a_d = act_desc + (uint32_t)(l * (16384 >> 4)), b_d = w_desc + (uint32_t)(l * (8192 >> 4));
-#pragma unroll
-						for (int k = 0; k < 4; ++k)
-							mma_ss_lh(d_issue, a_d + k * 2, b_d + k * 2, dhi, l < 5 ? id_fwd64 : id_fwd16, k > 0);
-						tc_commit(d_full);
-					}
-					// ---- backward, per layer: dA first (critical path: delta_{l-1} = (delta_l W_l) * [a_l > 0]), then
-					// dW_l += delta_l^T a_l, which the tensor pipe executes while the epilogue of dA runs.
-#pragma unroll
-					for (int l = 5; l >= 0; --l) {
-						mbar_wait(a_ready, ar_ph); // delta_l stored
-						ar_ph ^= 1;
-						tc_fence_after();
-						const uint32_t dl = del_desc + (uint32_t)(((5 - l) & 1) * (16384 >> 4));
-						const uint32_t al = act_desc + (uint32_t)(l * (16384 >> 4)), wl = w_desc + (uint32_t)(l * (8192 >> 4));
-						if (l == 5) {
-							mma_ss_lh(d_issue, dl, wl, dhi, id_da, 0);
-							tc_commit(d_full);
-#pragma unroll
-							for (int k = 0; k < 8; ++k)
-								mma_ss_lh(tmem + kColDW5, al + k * 128, dl + k * 128, dhi, id_dw5t, (j > 0) || (k > 0));
-						} else {
-							if (l > 0) {
-#pragma unroll
-								for (int k = 0; k < 4; ++k)
-									mma_ss_lh(d_issue, dl + k * 2, wl + k * 128, dhi, id_da, k > 0);
-								tc_commit(d_full);
+						if (has_f) { // ---- forward layer k of tile r
+							if (IN_MODE == NRC_IN_ENCODED && k == 0) {
+								mbar_wait(in_full, in_ph);
+								in_ph ^= 1;
+							} else {
+								mbar_wait(af_ready, af_ph);
+								af_ph ^= 1;
 							}
+							tc_fence_after();
+							const uint32_t a_d = pool_desc + fw[k] * (16384 >> 4), b_d = w_desc + (uint32_t)(k * (8192 >> 4));
 #pragma unroll
-							for (int k = 0; k < 8; ++k)
-								mma_ss_lh(tmem + 64 * l, dl + k * 128, al + k * 128, dhi, id_dw64, (j > 0) || (k > 0));
-							if (l == 0) {
-								tc_commit(tile_done);
-								if (IN_MODE == NRC_IN_ENCODED && j + 1 < my_tiles) { // a_0 is free once dW_0 has consumed it
-									mbar_wait(tile_done, T & 1);
-									mbar_arrive_expect_tx(in_full, 16384);
-									tma_load_2d(act_sm, &tm_in, 0, (int32_t)((blockIdx.x + (j + 1) * gridDim.x) * NRC_TILE), in_full);
+							for (int kk = 0; kk < 4; ++kk)
+								mma_ss_lh(df_issue, a_d + kk * 2, b_d + kk * 2, dhi, k < 5 ? id_fwd64 : id_fwd16, kk > 0);
+							tc_commit(df_full);
+						}
+						if (has_b) { // ---- backward layer l of tile r - 1: dA first (critical path), then dW_l
+							if (l < 5) {
+								mbar_wait(ab_ready, ab_ph); // delta_l stored
+								ab_ph ^= 1;
+							}
+							tc_fence_after();
+							const uint32_t dl = del_desc + (uint32_t)(((5 - l) & 1) * (16384 >> 4));
+							const uint32_t al = pool_desc + bw[l] * (16384 >> 4), wl = w_desc + (uint32_t)(l * (8192 >> 4));
+							const uint32_t acc = (r > 1) ? 1u : 0u; // dW accumulates from the CTA's second tile on
+							if (l == 5) {
+								mma_ss_lh(db_issue, dl, wl, dhi, id_da, 0);
+								tc_commit(db_full);
+#pragma unroll
+								for (int kk = 0; kk < 8; ++kk)
+									mma_ss_lh(tmem + kColDW5, al + kk * 128, dl + kk * 128, dhi, id_dw5t, acc | (kk > 0));
+							} else {
+								if (l > 0) {
+#pragma unroll
+									for (int kk = 0; kk < 4; ++kk)
+										mma_ss_lh(db_issue, dl + kk * 2, wl + kk * 128, dhi, id_da, kk > 0);
+									tc_commit(db_full);
 								}
+#pragma unroll
+								for (int kk = 0; kk < 8; ++kk)
+									mma_ss_lh(tmem + 64 * l, dl + kk * 128, al + kk * 128, dhi, id_dw64, acc | (kk > 0));
+								if (l == 0)
+									tc_commit(tile_done);
+								if (IN_MODE == NRC_IN_ENCODED && l == 1)
+									tc_commit(dw1_done);
 							}
 						}
+						if (IN_MODE == NRC_IN_ENCODED && k == 5 && r + 1 < my_tiles) {
+							// a_0 of tile r + 1 goes to the buffer of a_1 of tile r - 1 (bw[1]), free once dW_1 (step 4) has read it
+							if (has_b) {
+								mbar_wait(dw1_done, dw1_ph);
+								dw1_ph ^= 1;
+							}
+							mbar_arrive_expect_tx(in_full, 16384);
+							tma_load_2d(pool_sm + bw[1] * 16384, &tm_in, 0, (int32_t)((blockIdx.x + (r + 1) * gridDim.x) * NRC_TILE), in_full);
+						}
 					}
-				}
+					rotate_tiles();
+				};
+				issue_round(std::true_type{}, std::false_type{}, 0u);
+#pragma unroll 1
+				for (uint32_t r = 1; r < my_tiles; ++r)
+					issue_round(std::true_type{}, std::true_type{}, r);
+				issue_round(std::false_type{}, std::true_type{}, my_tiles);
 			}
 			__syncwarp();
 		} else {
@@ -423,169 +478,183 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			float loss_acc = 0.0f;
 			uint32_t valid_rows = 0;
 			// Draining a finished dW accumulator (M=64 TMEM layout: row r -> lane (r%16) + 32*(r/16)): TMEM -> fp32 staging
-			// in the (by then dead) shared-memory tile of a_l, 16-byte chunks XOR-swizzled per row against bank conflicts
-			// -> fully coalesced copy to this CTA's partial. For all but the last two layers this runs inside the backward
-			// pass of the CTA's last tile, in the time the epilogue warps would spend waiting for the next accumulator.
-			float *stage = (float *)act_sm;
-			auto stage_dw = [&](int l) {
+			// in a dead pool buffer, 16-byte chunks XOR-swizzled per row against bank conflicts -> fully coalesced copy to
+			// this CTA's partial. For all but the last two layers this runs inside the backward pass of the CTA's last tile,
+			// in the time the epilogue warps would spend waiting for the next accumulator.
+			auto stage_dw = [&](int l, float *stage) {
 				uint32_t v[32];
 				tmem_ld_x32(tmem_addr(tmem, q * 32, 64 * l + 32 * h), v);
 				tc_wait_ld();
 				if (lane < 16) {
 					const uint32_t r = q * 16 + lane;
-					float4 *dst = (float4 *)(stage + l * 4096 + r * 64);
+					float4 *dst = (float4 *)(stage + r * 64);
 #pragma unroll
 					for (int i = 0; i < 8; ++i)
 						dst[(8 * h + i) ^ (r & 7)] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
 						                                        __uint_as_float(v[4 * i + 3]));
 				}
 			};
-			auto copy_out = [&](uint32_t first4, uint32_t count4) { // float4 indices into the partial (layers 0..4: swizzled staging)
+			auto copy_layer = [&](int l, const float *stage) { // 1024 float4 of dW_l: swizzled staging -> the partial
 				const float4 *stage4 = (const float4 *)stage;
-				float4 *out4 = (float4 *)my_partial;
-				for (uint32_t idx = first4 + threadIdx.x; idx < first4 + count4; idx += kEpiThreads) {
+				float4 *out4 = (float4 *)my_partial + l * 1024;
+				for (uint32_t idx = threadIdx.x; idx < 1024; idx += kEpiThreads) {
 					const uint32_t r = (idx >> 4) & 63u;
 					out4[idx] = stage4[(idx & ~15u) | ((idx & 15u) ^ (r & 7u))];
 				}
 			};
-#pragma unroll 1
-			for (uint32_t j = 0; j < my_tiles; ++j) {
-				const uint32_t T = tile_base + j;
-				const uint32_t tile = blockIdx.x + j * gridDim.x;
-				const uint64_t gi = (uint64_t)tile * NRC_TILE + row;
-				const bool valid = gi < n;
-				float tgt[3] = {0.0f, 0.0f, 0.0f};
-				if (h == 0 && valid && IN_MODE != NRC_IN_IMAGE_RANDOM) { // loaded first: the latency hides under the forward pass
-					if (p.target_is_f16) {
-						const __half *t = (const __half *)((const uint8_t *)p.target + gi * p.target_stride_bytes);
-						tgt[0] = __half2float(t[0]), tgt[1] = __half2float(t[1]), tgt[2] = __half2float(t[2]);
-					} else {
-						const float *t = (const float *)((const uint8_t *)p.target + gi * p.target_stride_bytes);
-						tgt[0] = t[0], tgt[1] = t[1], tgt[2] = t[2];
+			uint32_t fin1 = 1, fin0 = 0;        // staging buffers of dW_1 / dW_0 (the last tile's a_1 / a_0 buffers)
+			float tgt[3] = {0.0f, 0.0f, 0.0f}; // the forward tile's target (loaded at step 0, used at step 5)
+			bool valid_f = false;
+			uint64_t gi_f = 0;
+			auto epilogue_round = [&](auto HF, auto HB, uint32_t r) {
+				constexpr bool has_f = decltype(HF)::value, has_b = decltype(HB)::value, last_round = !has_f;
+				if (has_f) {
+					const uint32_t tile = blockIdx.x + r * gridDim.x;
+					gi_f = (uint64_t)tile * NRC_TILE + row;
+					valid_f = gi_f < n;
+					tgt[0] = tgt[1] = tgt[2] = 0.0f;
+					if (h == 0 && valid_f && IN_MODE != NRC_IN_IMAGE_RANDOM) { // loaded first: the latency hides under the forward pass
+						if (p.target_is_f16) {
+							const __half *t = (const __half *)((const uint8_t *)p.target + gi_f * p.target_stride_bytes);
+							tgt[0] = __half2float(t[0]), tgt[1] = __half2float(t[1]), tgt[2] = __half2float(t[2]);
+						} else {
+							const float *t = (const float *)((const uint8_t *)p.target + gi_f * p.target_stride_bytes);
+							tgt[0] = t[0], tgt[1] = t[1], tgt[2] = t[2];
+						}
 					}
-				}
-				if (IN_MODE == NRC_IN_IMAGE_RANDOM && h == 0 && valid) { // target = the image at this sample's uv (gradient.comp:47-50)
-					uint32_t px = p.seed_x + (uint32_t)(gi % 128u), py = p.seed_y + (uint32_t)(gi / 128u);
-					pcg2d(px, py);
-					const float sc = 1.0f / (float)0xffffffffu;
-					sample_bilinear_rgb(p.image_rgba8, p.image_w, p.image_h, sc * (float)px, sc * (float)py, tgt);
-				}
-				if (IN_MODE != NRC_IN_ENCODED && j > 0) { // (tile 0 was encoded ahead of time)
-					mbar_wait(tile_done, (T - 1) & 1); // the previous tile's dW_0 MMA still reads a_0
-					encode_tile_row(p, n, tile);
-					arrive_a_ready();
+					if (IN_MODE == NRC_IN_IMAGE_RANDOM && h == 0 && valid_f) { // target = the image at this sample's uv (gradient.comp:47-50)
+						uint32_t px = p.seed_x + (uint32_t)(gi_f % 128u), py = p.seed_y + (uint32_t)(gi_f / 128u);
+						pcg2d(px, py);
+						const float sc = 1.0f / (float)0xffffffffu;
+						sample_bilinear_rgb(p.image_rgba8, p.image_w, p.image_h, sc * (float)px, sc * (float)py, tgt);
+					}
 				}
 				NRC_GTRACE(3);
-				// -------------------------------------------------------------------------------------- forward
-#ifdef NRC_TRAIN_NO_EPI_UNROLL
-#pragma unroll 1
-#else
 #pragma unroll
-#endif
-				for (int l = 0; l < NRC_LAYERS; ++l) {
-					mbar_wait(d_full, d_ph);
-					d_ph ^= 1;
-					tc_fence_after();
-					NRC_GTRACE(0x10 + l);
-					if (l < NRC_HIDDEN_LAYERS) { // a_{l+1} = fp16(relu(D))
-						uint32_t v[32], o[16];
-						tmem_ld_x32(d_mine, v);
-						tc_wait_ld();
+				for (int k = 0; k < NRC_LAYERS; ++k) {
+					const int l = 5 - k;
+					if (has_f) { // ------------------------------------------------------------ forward epilogue, layer k
+						mbar_wait(df_full, df_ph);
+						df_ph ^= 1;
+						tc_fence_after();
+						NRC_GTRACE(0x10 + k);
+						if (k < NRC_HIDDEN_LAYERS) { // a_{k+1} = fp16(relu(D))
+							uint32_t v[32], o[16];
+							tmem_ld_x32(df_mine, v);
+							tc_wait_ld();
 #pragma unroll
-						for (int i = 0; i < 16; ++i)
-							o[i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-						store_half_row(act_sm + (l + 1) * 16384, o);
-					} else if (h == 0) { // output layer + loss gradient (NN_nv.glsl:148-196)
-						uint32_t yv[4];
-						tmem_ld_x4(tmem_addr(tmem, q * 32, kColWork), yv);
-						tc_wait_ld();
-						float y[3], g[3]; // y is the fp16 network output widened to fp32, as NNOutput3 returns it
-#pragma unroll
-						for (int c = 0; c < 3; ++c)
-							y[c] = __half2float(__float2half_rn(__uint_as_float(yv[c])));
-						float inv_den = 1.0f;
-						if (p.loss_kind == NRC_LOSS_RELATIVE_L2_LUMINANCE) {
-							const float lum = 0.299f * fmaxf(y[0], 0.0f) + 0.587f * fmaxf(y[1], 0.0f) + 0.114f * fmaxf(y[2], 0.0f);
-							inv_den = __frcp_rn(lum * lum + 0.01f); // one correctly rounded reciprocal instead of six divisions
-						}
-#pragma unroll
-						for (int c = 0; c < 3; ++c) {
-							const float d = y[c] - tgt[c];
-							g[c] = 2.0f * p.loss_scale * d * inv_den;
-							if (valid)
-								loss_acc += d * d * inv_den;
-						}
-						if (!valid)
-							g[0] = g[1] = g[2] = 0.0f;
-						valid_rows += valid ? 1u : 0u;
-						if (valid && p.y_out) {
-							float *yo = (float *)p.y_out + 3 * gi;
-							yo[0] = y[0], yo[1] = y[1], yo[2] = y[2];
-						}
-						uint8_t *r = delta_sm + row * 128; // delta_5: 16 fp16 = logical chunks 0 and 1 of the row
-						*(uint4 *)(r + ((0 ^ (row & 7)) << 4)) = make_uint4(cvt_pack_f16x2(g[0], g[1]), cvt_pack_f16x2(g[2], 0.0f), 0u, 0u);
-						*(uint4 *)(r + ((1 ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
-					}
-					NRC_GTRACE(0x20 + l);
-					arrive_a_ready();
-				}
-				// -------------------------------------------------------------------------------------- backward
-#ifdef NRC_TRAIN_NO_EPI_UNROLL
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
-				for (int l = 5; l >= 1; --l) { // delta_{l-1} = fp16(D) * [a_l > 0], NaN -> 0 (NN_nv.glsl:198-220, 240-242)
-					mbar_wait(d_full, d_ph);
-					d_ph ^= 1;
-					tc_fence_after();
-					NRC_GTRACE(0x30 + l);
-					uint32_t v[32], a[16], o[16];
-					tmem_ld_x32(d_mine, v);
-					{
-						const uint8_t *r = act_sm + l * 16384 + row * 128;
-#pragma unroll
-						for (int c = 0; c < 4; ++c) {
-							const uint4 t = *(const uint4 *)(r + (((4 * h + c) ^ (row & 7)) << 4));
-							a[4 * c] = t.x, a[4 * c + 1] = t.y, a[4 * c + 2] = t.z, a[4 * c + 3] = t.w;
-						}
-					}
-					tc_wait_ld();
-#pragma unroll
-					for (int i = 0; i < 16; ++i) {
-						const uint32_t d2 = cvt_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-						const __half2 dh = *(const __half2 *)&d2, ah = *(const __half2 *)&a[i];
-						o[i] = d2 & __hgt2_mask(ah, __float2half2_rn(0.0f)) & __heq2_mask(dh, dh);
-					}
-					store_half_row(delta_sm + ((5 - (l - 1)) & 1) * 16384, o);
-					NRC_GTRACE(0x40 + l);
-					arrive_a_ready();
-					if (j + 1 == my_tiles && l <= 4) { // dW_{l+1} is final (its MMAs precede this step's commit): drain it now
-						if (l == 4) {
+							for (int i = 0; i < 16; ++i)
+								o[i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+							store_half_row(pool_sm + fw[k + 1] * 16384, o);
+							NRC_GTRACE(0x20 + k);
+							arrive_ready(af_ready);
+						} else { // output layer + loss gradient (NN_nv.glsl:148-196) -> delta_5
 							if (h == 0) {
-								uint32_t v5[4];
-								tmem_ld_x4(tmem_addr(tmem, q * 32, kColDW5), v5); // dW_5^T: lane <-> in, column <-> out
+								uint32_t yv[4];
+								tmem_ld_x4(tmem_addr(tmem, q * 32, kColWorkF), yv);
 								tc_wait_ld();
-								if (lane < 16) {
-									float *dst = my_partial + 5 * 4096 + q * 16 + lane;
-									dst[0] = __uint_as_float(v5[0]), dst[64] = __uint_as_float(v5[1]), dst[128] = __uint_as_float(v5[2]);
+								float y[3], g[3]; // y is the fp16 network output widened to fp32, as NNOutput3 returns it
+#pragma unroll
+								for (int c = 0; c < 3; ++c)
+									y[c] = __half2float(__float2half_rn(__uint_as_float(yv[c])));
+								float inv_den = 1.0f;
+								if (p.loss_kind == NRC_LOSS_RELATIVE_L2_LUMINANCE) {
+									const float lum = 0.299f * fmaxf(y[0], 0.0f) + 0.587f * fmaxf(y[1], 0.0f) + 0.114f * fmaxf(y[2], 0.0f);
+									inv_den = __frcp_rn(lum * lum + 0.01f); // one correctly rounded reciprocal instead of six divisions
 								}
+#pragma unroll
+								for (int c = 0; c < 3; ++c) {
+									const float d = y[c] - tgt[c];
+									g[c] = 2.0f * p.loss_scale * d * inv_den;
+									if (valid_f)
+										loss_acc += d * d * inv_den;
+								}
+								if (!valid_f)
+									g[0] = g[1] = g[2] = 0.0f;
+								valid_rows += valid_f ? 1u : 0u;
+								if (valid_f && p.y_out) {
+									float *yo = (float *)p.y_out + 3 * gi_f;
+									yo[0] = y[0], yo[1] = y[1], yo[2] = y[2];
+								}
+								uint8_t *rr = delta_sm + row * 128; // delta_5 (buffer 0): 16 fp16 = logical chunks 0 and 1 of the row
+								*(uint4 *)(rr + ((0 ^ (row & 7)) << 4)) = make_uint4(cvt_pack_f16x2(g[0], g[1]), cvt_pack_f16x2(g[2], 0.0f), 0u, 0u);
+								*(uint4 *)(rr + ((1 ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
 							}
-						} else {
-							stage_dw(l + 1);
-							asm volatile("bar.sync 1, 256;" ::: "memory");
-							copy_out((l + 1) * 1024, 1024);
+							NRC_GTRACE(0x25);
+							arrive_ready(d5_ready); // delta_5 feeds backward layer 5 (step 0 of the next round)
+							if (IN_MODE != NRC_IN_ENCODED && r + 1 < my_tiles) {
+								// a_0 of tile r + 1 -> the buffer of a_1 of tile r - 1 (bw[1]): its last reader (dW_1, step 4) was issued
+								// before this step's forward MMAs, whose commit has just been observed
+								encode_tile_row(p, n, blockIdx.x + (r + 1) * gridDim.x, pool_sm + bw[1] * 16384);
+								arrive_ready(af_ready);
+							}
+						}
+					}
+					if (has_b && l >= 1) { // --------------------------------------------------- backward epilogue, layer l
+						// delta_{l-1} = fp16(D) * [a_l > 0], NaN -> 0 (NN_nv.glsl:198-220, 240-242)
+						mbar_wait(db_full, db_ph);
+						db_ph ^= 1;
+						tc_fence_after();
+						NRC_GTRACE(0x30 + l);
+						uint32_t v[32], a[16], o[16];
+						tmem_ld_x32(db_mine, v);
+						{
+							const uint8_t *rr = pool_sm + bw[l] * 16384 + row * 128;
+#pragma unroll
+							for (int c = 0; c < 4; ++c) {
+								const uint4 t = *(const uint4 *)(rr + (((4 * h + c) ^ (row & 7)) << 4));
+								a[4 * c] = t.x, a[4 * c + 1] = t.y, a[4 * c + 2] = t.z, a[4 * c + 3] = t.w;
+							}
+						}
+						tc_wait_ld();
+#pragma unroll
+						for (int i = 0; i < 16; ++i) {
+							const uint32_t d2 = cvt_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+							const __half2 dh = *(const __half2 *)&d2, ah = *(const __half2 *)&a[i];
+							o[i] = d2 & __hgt2_mask(ah, __float2half2_rn(0.0f)) & __heq2_mask(dh, dh);
+						}
+						store_half_row(delta_sm + ((6 - l) & 1) * 16384, o);
+						NRC_GTRACE(0x40 + l);
+						arrive_ready(ab_ready);
+						if (last_round && l <= 4) { // dW_{l+1} is final (its MMAs precede this step's commits): drain it now
+							if (l == 4) {
+								if (h == 0) {
+									uint32_t v5[4];
+									tmem_ld_x4(tmem_addr(tmem, q * 32, kColDW5), v5); // dW_5^T: lane <-> in, column <-> out
+									tc_wait_ld();
+									if (lane < 16) {
+										float *dst = my_partial + 5 * 4096 + q * 16 + lane;
+										dst[0] = __uint_as_float(v5[0]), dst[64] = __uint_as_float(v5[1]), dst[128] = __uint_as_float(v5[2]);
+									}
+								}
+							} else { // staging: the dead tile of a_{l+1} (its last reader was dW_{l+1} itself)
+								float *stage = (float *)(pool_sm + bw[l + 1] * 16384);
+								stage_dw(l + 1, stage);
+								asm volatile("bar.sync 1, 256;" ::: "memory");
+								copy_layer(l + 1, stage);
+							}
 						}
 					}
 				}
-			}
-			// ---- the last two layers' dW complete with tile_done (dW_5..dW_2 were drained during the backward pass)
+				if (last_round)
+					fin1 = bw[1], fin0 = bw[0];
+				rotate_tiles();
+			};
+			epilogue_round(std::true_type{}, std::false_type{}, 0u);
+#pragma unroll 1
+			for (uint32_t r = 1; r < my_tiles; ++r)
+				epilogue_round(std::true_type{}, std::true_type{}, r);
+			epilogue_round(std::false_type{}, std::true_type{}, my_tiles);
+			// ---- the last two layers' dW complete with tile_done (dW_5..dW_2 were drained during the backward pass); they are
+			// staged in the last tile's a_1 / a_0 buffers (dead once every MMA has completed, and distinct from the buffers
+			// the earlier drains may still be copied out of by slower warps)
 			NRC_GTRACE(5);
 			mbar_wait(tile_done, (tile_base + my_tiles - 1) & 1);
 			tc_fence_after();
 			NRC_GTRACE(6);
-			stage_dw(1);
-			stage_dw(0);
+			float *stage1 = (float *)(pool_sm + fin1 * 16384), *stage0 = (float *)(pool_sm + fin0 * 16384);
+			stage_dw(1, stage1);
+			stage_dw(0, stage0);
 			// loss / count slots: fixed-order reduction over the four h == 0 warps (deterministic)
 			float cnt = (float)valid_rows;
 #pragma unroll
@@ -598,7 +667,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			tc_fence_before();
 			asm volatile("bar.sync 1, 256;" ::: "memory");
 			NRC_GTRACE(7);
-			copy_out(0, 2048); // dW_0, dW_1
+			copy_layer(1, stage1);
+			copy_layer(0, stage0);
 			if (threadIdx.x < (NRC_GRAD_STRIDE - NRC_WEIGHT_COUNT) / 4) { // loss, count, zero padding
 				float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 				if (threadIdx.x == 0)
@@ -609,9 +679,9 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		}
 		if (IN_MODE != NRC_IN_ENCODED && warp < kEpiWarps && tiles_next) { // encode the next batch's first tile now
 			if (my_tiles)
-				asm volatile("bar.sync 1, 256;" ::: "memory"); // every thread is done reading the staged dW_0 (a_0's tile)
-			encode_tile_row(tp.batch[b + 1], n_next, blockIdx.x);
-			arrive_a_ready();
+				asm volatile("bar.sync 1, 256;" ::: "memory"); // every thread is done reading the staged dW (pool buffers 0 and 1)
+			encode_tile_row(tp.batch[b + 1], n_next, blockIdx.x, pool_sm);
+			arrive_ready(af_ready);
 		}
 		tile_base += my_tiles;
 		w_reloads += (b > 0 && my_tiles) ? 1u : 0u;
@@ -786,13 +856,13 @@ static cudaError_t launch_train_t(const TrainParams &p, const CUtensorMap &tm_w,
 	auto kern = nrc_train_kernel<IN_MODE>;
 	static bool configured = false;
 	if (!configured) {
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kTrainSmemBytes);
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, train_smem_bytes(8));
 		if (e != cudaSuccess)
 			return e;
 		configured = true;
 	}
 	cudaLaunchConfig_t cfg{};
-	cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kTrainThreads), cfg.dynamicSmemBytes = kTrainSmemBytes, cfg.stream = stream;
+	cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kTrainThreads), cfg.dynamicSmemBytes = train_smem_bytes(p.pool_tiles), cfg.stream = stream;
 	cudaLaunchAttribute attr[1];
 	attr[0].id = cudaLaunchAttributeCooperative; // the grid barrier needs every CTA resident
 	attr[0].val.cooperative = 1;
@@ -809,15 +879,17 @@ cudaError_t launch_train(const TrainParams &p, const CUtensorMap &tm_w, const CU
 	const uint32_t grid = (uint32_t)(ntiles < (uint64_t)sms ? ntiles : (uint64_t)sms);
 	if (grid_out)
 		*grid_out = grid;
+	TrainParams q = p;
+	q.pool_tiles = ntiles > grid ? 8u : 6u; // two tiles in flight only where a CTA has more than one
 	switch (p.batch[0].in_mode) {
 	case NRC_IN_ENCODED:
-		return launch_train_t<NRC_IN_ENCODED>(p, tm_w, tm_in, grid, stream);
+		return launch_train_t<NRC_IN_ENCODED>(q, tm_w, tm_in, grid, stream);
 	case NRC_IN_UNPACKED:
-		return launch_train_t<NRC_IN_UNPACKED>(p, tm_w, tm_in, grid, stream);
+		return launch_train_t<NRC_IN_UNPACKED>(q, tm_w, tm_in, grid, stream);
 	case NRC_IN_IMAGE_RANDOM:
-		return launch_train_t<NRC_IN_IMAGE_RANDOM>(p, tm_w, tm_in, grid, stream);
+		return launch_train_t<NRC_IN_IMAGE_RANDOM>(q, tm_w, tm_in, grid, stream);
 	case NRC_IN_PACKED:
-		return launch_train_t<NRC_IN_PACKED>(p, tm_w, tm_in, grid, stream);
+		return launch_train_t<NRC_IN_PACKED>(q, tm_w, tm_in, grid, stream);
 	}
 	return cudaErrorInvalidValue;
 }
