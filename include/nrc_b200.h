@@ -121,6 +121,11 @@ int nrc_infer(nrc_handle_t h, const void *d_eval_records, const uint32_t *d_coun
 int nrc_infer_packed(nrc_handle_t h, const void *d_packed_inputs, uint32_t stride_bytes, const uint32_t *d_count,
                      uint64_t max_count, const NrcScene *scene, void *d_outputs_f16vec3, void *stream);
 /* UnpackNRCInput on its own (NRCRecord.glsl:98-125): PackedNRCInput words -> [n][14] fp32 in UnpackedNRCInput order. */
+/* Flattens the scene's index buffers into NrcScene::prim_table rows (64 B per primitive, 64-byte aligned, caller-owned
+ * device memory of nrc_scene_prim_table_bytes(prim_count)). Once per scene: the reference never edits geometry after
+ * load (src/VkScene.cpp:64-133). `scene->prim_table` itself is ignored here. */
+uint64_t nrc_scene_prim_table_bytes(uint32_t prim_count);
+int nrc_scene_build_prim_table(const NrcScene *scene, uint32_t prim_count, void *d_prim_table, void *stream);
 int nrc_unpack_inputs(const void *d_packed_inputs, uint32_t stride_bytes, uint64_t n, const NrcScene *scene,
                       float *d_unpacked14, void *stream);
 int nrc_gradient(nrc_handle_t h, const void *d_train_records, uint32_t *d_count, uint32_t max_count,

@@ -51,7 +51,16 @@ typedef struct NrcScene {
 	const float *transforms;          /* mat3x4 per instance = 3 vec4 columns {r0.xyz t.x | r1.xyz t.y | r2.xyz t.z} (VkScene.cpp:63-71) */
 	const NrcTexture *textures;       /* device array of descriptors */
 	uint32_t texture_count;
+	/* Optional (NULL = gather through the index buffers as the reference does): NrcPrimRow per primitive, built once per
+	 * scene by nrc_scene_build_prim_table - one 64-byte line instead of 7 index + 15 attribute loads on two dependent
+	 * levels. The values are copies, so results are bit-identical either way. */
+	const void *prim_table;
 } NrcScene;
+typedef struct NrcPrimRow { /* 64 B, 64-byte aligned */
+	float v[3][3];        /* object-space vertices (GetSceneVertex, Scene.glsl:50-52) */
+	float tc[3][2];       /* texture coordinates (GetSceneTexcoord, Scene.glsl:53-56) */
+	uint32_t material_id;
+} NrcPrimRow;
 typedef struct NrcOptimizerState { /* src/VkNRCState.cpp:25-28, 20 B */
 	uint32_t t;
 	float beta1_t, beta2_t, alpha_t, alpha_t_1;

@@ -64,6 +64,17 @@ def test_unpack_matches_oracle(nrc, oracle_mod):
     assert np.abs(got - oracle_mod.unpack(sc, pk)).max() <= 2e-5
 
 
+def test_prim_table_gather_is_bit_identical(nrc):
+    """NrcScene::prim_table (the per-primitive 64-byte rows built by nrc_scene_build_prim_table) only changes where the
+    gather reads its values from: the unpacked inputs must match the index-buffer gather bit for bit."""
+    sc = make_scene(23)
+    args = (sc.vertices, sc.vertex_indices, sc.texcoords, sc.texcoord_indices, sc.materials, sc.material_ids, sc.transforms, sc.textures)
+    flat, indexed = nrc.DeviceScene(*args, prim_table=True), nrc.DeviceScene(*args, prim_table=False)
+    assert flat.c.prim_table and not indexed.c.prim_table
+    pk = dev(random_packed_inputs(29, 20000, sc))
+    assert torch.equal(nrc.unpack_inputs(pk, flat), nrc.unpack_inputs(pk, indexed))
+
+
 def test_infer_packed_matches_oracle(nrc, oracle_mod, state):
     sc = make_scene(11)
     dsc = upload_scene(nrc, sc)

@@ -45,14 +45,17 @@ class nrc_texture_t(C.Structure):  # include/nrc_b200_types.h NrcTexture
 class nrc_scene_t(C.Structure):  # include/nrc_b200_types.h NrcScene (device pointers)
     _fields_ = [("vertices", C.c_void_p), ("vertex_indices", C.c_void_p), ("texcoords", C.c_void_p), ("texcoord_indices", C.c_void_p),
                 ("materials", C.c_void_p), ("material_ids", C.c_void_p), ("transforms", C.c_void_p), ("textures", C.c_void_p),
-                ("texture_count", C.c_uint32)]
+                ("texture_count", C.c_uint32), ("prim_table", C.c_void_p)]
 
 
 class DeviceScene:
     """Uploads scene buffers given in the reference's layouts (numpy arrays; see shader/src/Scene.glsl:8-71) and holds
     the NrcScene struct of device pointers that the record-format entry points take."""
 
-    def __init__(self, vertices, vertex_indices, texcoords, texcoord_indices, materials, material_ids, transforms, textures, device=0):
+    def __init__(self, vertices, vertex_indices, texcoords, texcoord_indices, materials, material_ids, transforms, textures, device=0,
+                 prim_table: bool = True):
+        """prim_table: also build the per-primitive 64-byte rows (nrc_scene_build_prim_table) that turn the two-level
+        index -> attribute gather of UnpackNRCInput into one aligned line (results are bit-identical)."""
         import torch
         dev = f"cuda:{device}"
 
@@ -69,7 +72,14 @@ class DeviceScene:
         k = self._keep
         self.c = nrc_scene_t(k["vertices"].data_ptr(), k["vertex_indices"].data_ptr(), k["texcoords"].data_ptr(), k["texcoord_indices"].data_ptr(),
                              k["materials"].data_ptr(), k["material_ids"].data_ptr(), k["transforms"].data_ptr(), self._table.data_ptr(),
-                             len(textures))
+                             len(textures), None)
+        if prim_table:
+            n_prims = int(np.asarray(material_ids).shape[0])
+            self._prims = torch.empty(max(64, lib().nrc_scene_prim_table_bytes(n_prims)), dtype=torch.uint8, device=dev)
+            assert self._prims.data_ptr() % 64 == 0
+            with torch.cuda.device(device):
+                _check(lib().nrc_scene_build_prim_table(C.byref(self.c), n_prims, self._prims.data_ptr(), _stream()))
+            self.c.prim_table = self._prims.data_ptr()
 
 
 class NrcError(RuntimeError):
@@ -137,6 +147,8 @@ SIGNATURES = {
     "nrc_image_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.c_float, C.c_void_p]),
     "nrc_infer_encoded_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
+    "nrc_scene_prim_table_bytes": (C.c_uint64, [C.c_uint32]),
+    "nrc_scene_build_prim_table": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "nrc_image_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
 }
 

@@ -48,13 +48,14 @@ __device__ unsigned int g_nrc_trace_n[4];
 namespace nrc {
 
 // Shared memory: weights (6 x 8 KB), two 16 KB input buffers per slot, barriers.
+constexpr uint32_t kSmemTextures = 64; // texture descriptors staged in shared memory when the scene has no more than this
 template <int NT, int IN_MODE> struct InferSmem {
 	static constexpr uint32_t kWeightBytes = NRC_LAYERS * 8192;
 	static constexpr uint32_t kInOff = kWeightBytes;
 	static constexpr uint32_t kInBytes = NT * 2 * 16384;
 	static constexpr uint32_t kBarOff = kInOff + kInBytes;
 	static constexpr uint32_t kLutOff = kBarOff + 256; // sRGB -> linear table (packed records only)
-	static constexpr uint32_t kLutBytes = IN_MODE == NRC_IN_PACKED ? 1024 : 0;
+	static constexpr uint32_t kLutBytes = IN_MODE == NRC_IN_PACKED ? 1024 + kSmemTextures * 16 : 0; // + texture descriptors
 #ifdef NRC_TRACE
 	static constexpr uint32_t kTraceOff = kLutOff + kLutBytes;
 	static constexpr uint32_t kBytes = kTraceOff + 4 * NRC_TRACE_CAP * 8 + 1024;
@@ -140,7 +141,8 @@ template <int IN_MODE> __device__ __forceinline__ void load_raw(const InferParam
 	}
 }
 template <int IN_MODE>
-__device__ __forceinline__ void encode_raw(const InferParams &p, uint64_t gi, bool valid, const RawInput<IN_MODE> &r, uint32_t o[32], const float *lut) {
+__device__ __forceinline__ void encode_raw(const InferParams &p, uint64_t gi, bool valid, const RawInput<IN_MODE> &r, uint32_t o[32], const float *lut,
+                                           const NrcTexture *textures) {
 	if (IN_MODE == NRC_IN_IMAGE_GRID) { // uv = (coord + 0.5) / width  (inference.comp:33-34)
 		const uint32_t x = (uint32_t)(gi % p.image_width), y = (uint32_t)(gi / p.image_width);
 		encode_oneblob32(((float)x + 0.5f) / (float)p.image_width, ((float)y + 0.5f) / (float)p.image_width, o);
@@ -149,7 +151,7 @@ __device__ __forceinline__ void encode_raw(const InferParams &p, uint64_t gi, bo
 	float in[14];
 	if (IN_MODE == NRC_IN_PACKED) {
 		if (valid) {
-			unpack_nrc_input(p.scene, r.pk, in, lut);
+			unpack_nrc_input(p.scene, r.pk, in, lut, textures);
 		} else {
 #pragma unroll
 			for (int i = 0; i < 14; ++i)
@@ -193,8 +195,17 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 	const uint32_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
 
 	const float *lut = (const float *)(smem + L::kLutOff);
-	if (IN_MODE == NRC_IN_PACKED && threadIdx.x < 256)
-		((float *)(smem + L::kLutOff))[threadIdx.x] = kSrgbToLinear[threadIdx.x];
+	const NrcTexture *textures = p.scene.textures;
+	if (IN_MODE == NRC_IN_PACKED) {
+		if (threadIdx.x < 256)
+			((float *)(smem + L::kLutOff))[threadIdx.x] = kSrgbToLinear[threadIdx.x];
+		if (p.scene.texture_count <= kSmemTextures) {
+			NrcTexture *tsm = (NrcTexture *)(smem + L::kLutOff + 1024);
+			if (threadIdx.x < p.scene.texture_count)
+				tsm[threadIdx.x] = p.scene.textures[threadIdx.x];
+			textures = tsm;
+		}
+	}
 	if (threadIdx.x == 0) {
 		mbar_init(w_full, 1);
 		for (int i = 0; i < NT; ++i) {
@@ -237,7 +248,7 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 			if (u + NP < units)
 				load_raw<IN_MODE>(p, unit_gi(u + NP), unit_gi(u + NP) < n, raw_next);
 			uint32_t o[32];
-			encode_raw<IN_MODE>(p, gi, gi < n, raw, o, lut);
+			encode_raw<IN_MODE>(p, gi, gi < n, raw, o, lut, textures);
 			if (it >= 2) // the slot has finished layer 0 of the tile that used this buffer before
 				mbar_wait(in_free + 2 * s + b, ((it >> 1) - 1) & 1);
 			uint8_t *dst = smem + L::kInOff + (s * 2 + b) * 16384 + row * 128;
@@ -477,6 +488,30 @@ __global__ void __launch_bounds__(256) nrc_unpack_kernel(const void *packed, uin
 #pragma unroll
 	for (int k = 0; k < 7; ++k)
 		dst[k] = make_float2(in[2 * k], in[2 * k + 1]);
+}
+// nrc_scene_build_prim_table: one thread per primitive copies what UnpackNRCInput would gather into its 64-byte row
+__global__ void __launch_bounds__(256) nrc_prim_table_kernel(const NrcScene scene, uint32_t prim_count, NrcPrimRow *rows) {
+	const uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;
+	if (prim >= prim_count)
+		return;
+	NrcPrimRow r;
+	for (int k = 0; k < 3; ++k) {
+		const float *p = scene.vertices + 3 * (size_t)scene.vertex_indices[3 * (size_t)prim + k];
+		r.v[k][0] = p[0], r.v[k][1] = p[1], r.v[k][2] = p[2];
+		const float *t = scene.texcoords + 2 * (size_t)scene.texcoord_indices[3 * (size_t)prim + k];
+		r.tc[k][0] = t[0], r.tc[k][1] = t[1];
+	}
+	r.material_id = scene.material_ids[prim];
+	const float4 *src = (const float4 *)&r;
+	float4 *dst = (float4 *)(rows + prim);
+	for (int i = 0; i < 4; ++i)
+		dst[i] = src[i];
+}
+cudaError_t launch_prim_table(const NrcScene &scene, uint32_t prim_count, void *rows, cudaStream_t stream) {
+	if (prim_count == 0)
+		return cudaSuccess;
+	nrc_prim_table_kernel<<<(prim_count + 255) / 256, 256, 0, stream>>>(scene, prim_count, (NrcPrimRow *)rows);
+	return cudaGetLastError();
 }
 cudaError_t launch_unpack(const void *packed, uint32_t stride_bytes, uint64_t n, const NrcScene &scene, float *out14, cudaStream_t stream) {
 	if (n == 0)

@@ -561,6 +561,7 @@ static int check_scene(const NrcScene *sc) {
 	NRC_REQUIRE(sc->texture_count == 0 || sc->textures, "scene: texture table is null");
 	NRC_REQUIRE(((uintptr_t)sc->transforms & 15u) == 0 && ((uintptr_t)sc->materials & 15u) == 0 && ((uintptr_t)sc->texcoords & 7u) == 0,
 	            "scene: transforms / materials must be 16-byte aligned, texcoords 8-byte aligned");
+	NRC_REQUIRE(((uintptr_t)sc->prim_table & 63u) == 0, "scene: prim_table must be 64-byte aligned");
 	return NRC_OK;
 }
 
@@ -600,6 +601,19 @@ int nrc_infer_packed(nrc_handle_t h, const void *d_packed_inputs, uint32_t strid
 	return h->state.Infer(p, nullptr, h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
 }
 
+uint64_t nrc_scene_prim_table_bytes(uint32_t prim_count) { return (uint64_t)prim_count * sizeof(NrcPrimRow); }
+int nrc_scene_build_prim_table(const NrcScene *scene, uint32_t prim_count, void *d_prim_table, void *stream) {
+	if (prim_count == 0)
+		return NRC_OK;
+	int rc = check_scene(scene);
+	if (rc != NRC_OK)
+		return rc;
+	NRC_REQUIRE(d_prim_table && ((uintptr_t)d_prim_table & 63u) == 0, "nrc_scene_build_prim_table: the table must be 64-byte aligned device memory");
+	cudaError_t e = launch_prim_table(*scene, prim_count, d_prim_table, (cudaStream_t)stream);
+	if (e != cudaSuccess)
+		return set_error(NRC_ERR_CUDA, std::string("nrc_scene_build_prim_table: ") + cudaGetErrorString(e));
+	return NRC_OK;
+}
 int nrc_unpack_inputs(const void *d_packed_inputs, uint32_t stride_bytes, uint64_t n, const NrcScene *scene, float *d_unpacked14, void *stream) {
 	if (n == 0)
 		return NRC_OK;

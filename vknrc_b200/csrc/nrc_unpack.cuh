@@ -48,13 +48,20 @@ __device__ const float kSrgbToLinear[256] = {
 };
 // `lut` = the table above or a copy of it in shared memory (the fused kernels stage it once per CTA: 24 look-ups per
 // textured record are 24 scattered L1 requests from global memory, but cheap LDS from shared memory)
+// floor-modulo of an integer-valued float by the texture size, in floating point (a runtime integer modulo costs ~25
+// instructions): the quotient estimate can be off by one only when `f` is a multiple of `size`, which the two fix-ups catch
+__device__ __forceinline__ int wrap_repeat(float f, float size) {
+	float r = fmaf(-size, floorf(f * __frcp_rn(size)), f);
+	r = r >= size ? r - size : r;
+	r = r < 0.0f ? r + size : r;
+	return (int)r;
+}
 __device__ __forceinline__ void sample_texture_srgb_repeat(const NrcTexture *tex, float u, float v, float rgb[3], const float *lut) {
 	const uint32_t *p = (const uint32_t *)tex->texels_rgba8_srgb;
 	const int w = (int)tex->width, h = (int)tex->height;
 	const float x = u * (float)w - 0.5f, y = v * (float)h - 0.5f;
 	const float fx = floorf(x), fy = floorf(y), tx = x - fx, ty = y - fy;
-	int x0 = (int)fx % w, y0 = (int)fy % h;
-	x0 += x0 < 0 ? w : 0, y0 += y0 < 0 ? h : 0;
+	const int x0 = wrap_repeat(fx, (float)w), y0 = wrap_repeat(fy, (float)h);
 	const int x1 = x0 + 1 == w ? 0 : x0 + 1, y1 = y0 + 1 == h ? 0 : y0 + 1;
 	const uint32_t c00 = __ldg(p + y0 * w + x0), c10 = __ldg(p + y0 * w + x1), c01 = __ldg(p + y1 * w + x0), c11 = __ldg(p + y1 * w + x1);
 #pragma unroll
@@ -65,26 +72,44 @@ __device__ __forceinline__ void sample_texture_srgb_repeat(const NrcTexture *tex
 	}
 }
 
-__device__ __forceinline__ void unpack_nrc_input(const NrcScene &sc, const uint32_t pk[4], float out[14], const float *lut = kSrgbToLinear) {
+// `textures` = sc.textures or a copy of the descriptor table in shared memory (one dependent load level less)
+__device__ __forceinline__ void unpack_nrc_input(const NrcScene &sc, const uint32_t pk[4], float out[14], const float *lut = kSrgbToLinear,
+                                                 const NrcTexture *textures = nullptr) {
+	if (!textures)
+		textures = sc.textures;
 	const uint32_t prim = pk[0], instance = pk[1] & 0x7FFFFFFFu;
 	const bool flip = (pk[1] >> 31) != 0u;
 	const float4 *m = (const float4 *)sc.transforms + 3 * (size_t)instance; // vec4(v, 1) * mat3x4 = a dot product per column
 	const float4 m0 = __ldg(m), m1 = __ldg(m + 1), m2 = __ldg(m + 2);
-	float v[3][3], tc[3][2];
+	float o[3][3], v[3][3], tc[3][2]; // object-space vertices, world-space vertices, texture coordinates
+	uint32_t material_id;
+	if (sc.prim_table) { // one 64-byte row per primitive (nrc_scene_build_prim_table): four 16-byte loads, one level
+		const float4 *row = (const float4 *)sc.prim_table + 4 * (size_t)prim;
+		const float4 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2), r3 = __ldg(row + 3);
+		o[0][0] = r0.x, o[0][1] = r0.y, o[0][2] = r0.z, o[1][0] = r0.w, o[1][1] = r1.x, o[1][2] = r1.y, o[2][0] = r1.z, o[2][1] = r1.w, o[2][2] = r2.x;
+		tc[0][0] = r2.y, tc[0][1] = r2.z, tc[1][0] = r2.w, tc[1][1] = r3.x, tc[2][0] = r3.y, tc[2][1] = r3.z;
+		material_id = __float_as_uint(r3.w);
+	} else {
 #pragma unroll
-	for (int k = 0; k < 3; ++k) { // GetSceneVertex / GetSceneTexcoord (Scene.glsl:50-56)
-		const float *p = sc.vertices + 3 * (size_t)__ldg(sc.vertex_indices + 3 * (size_t)prim + k);
-		const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+		for (int k = 0; k < 3; ++k) { // GetSceneVertex / GetSceneTexcoord (Scene.glsl:50-56)
+			const float *p = sc.vertices + 3 * (size_t)__ldg(sc.vertex_indices + 3 * (size_t)prim + k);
+			o[k][0] = __ldg(p), o[k][1] = __ldg(p + 1), o[k][2] = __ldg(p + 2);
+			const float2 t = __ldg((const float2 *)sc.texcoords + __ldg(sc.texcoord_indices + 3 * (size_t)prim + k));
+			tc[k][0] = t.x, tc[k][1] = t.y;
+		}
+		material_id = __ldg(sc.material_ids + prim);
+	}
+#pragma unroll
+	for (int k = 0; k < 3; ++k) {
+		const float x = o[k][0], y = o[k][1], z = o[k][2];
 		v[k][0] = x * m0.x + y * m0.y + z * m0.z + m0.w;
 		v[k][1] = x * m1.x + y * m1.y + z * m1.z + m1.w;
 		v[k][2] = x * m2.x + y * m2.y + z * m2.z + m2.w;
-		const float2 t = __ldg((const float2 *)sc.texcoords + __ldg(sc.texcoord_indices + 3 * (size_t)prim + k));
-		tc[k][0] = t.x, tc[k][1] = t.y;
 	}
 	const float e1x = v[1][0] - v[0][0], e1y = v[1][1] - v[0][1], e1z = v[1][2] - v[0][2];
 	const float e2x = v[2][0] - v[0][0], e2y = v[2][1] - v[0][1], e2z = v[2][2] - v[0][2];
 	float nx = e1y * e2z - e1z * e2y, ny = e1z * e2x - e1x * e2z, nz = e1x * e2y - e1y * e2x;
-	const float inv = 1.0f / sqrtf(nx * nx + ny * ny + nz * nz);
+	const float inv = rsqrtf(nx * nx + ny * ny + nz * nz); // (2 ulp; the normal goes through atan2 / acos and a one-blob next)
 	nx *= inv, ny *= inv, nz *= inv;
 	if (flip)
 		nx = -nx, ny = -ny, nz = -nz;
@@ -96,16 +121,16 @@ __device__ __forceinline__ void unpack_nrc_input(const NrcScene &sc, const uint3
 	const float kPi = 3.14159265358979323846f;
 	out[5] = (nx == 0.0f && ny == 0.0f) ? 0.5f : 0.5f + atan2f(ny, nx) / (2.0f * kPi); // NRCSphEncode, :47-49
 	out[6] = acosf(fminf(fmaxf(nz, -1.0f), 1.0f)) / kPi;
-	const NrcMaterial *mat = sc.materials + __ldg(sc.material_ids + prim);
+	const NrcMaterial *mat = sc.materials + material_id;
 	const float4 md = __ldg((const float4 *)mat), ms = __ldg((const float4 *)mat + 1);
 	out[7] = __ldg(&mat->roughness);
 	const float u = tc[0][0] * bx + tc[1][0] * by + tc[2][0] * bz, w = tc[0][1] * bx + tc[1][1] * by + tc[2][1] * bz;
 	const uint32_t dtex = __float_as_uint(md.w), stex = __float_as_uint(ms.w);
 	out[8] = md.x, out[9] = md.y, out[10] = md.z, out[11] = ms.x, out[12] = ms.y, out[13] = ms.z;
 	if (dtex != 0xFFFFFFFFu) // GetSceneDiffuse / GetSceneSpecular (Scene.glsl:59-64)
-		sample_texture_srgb_repeat(sc.textures + dtex, u, w, out + 8, lut);
+		sample_texture_srgb_repeat(textures + dtex, u, w, out + 8, lut);
 	if (stex != 0xFFFFFFFFu)
-		sample_texture_srgb_repeat(sc.textures + stex, u, w, out + 11, lut);
+		sample_texture_srgb_repeat(textures + stex, u, w, out + 11, lut);
 }
 
 __device__ __forceinline__ void load_packed_input(const void *base, uint64_t index, uint32_t stride_bytes, uint32_t pk[4]) {
