@@ -94,6 +94,29 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Best effort: run this rank (and therefore first-touch its pinned host buffers) on the CPUs of the NUMA node its GPU
+    hangs off, so that N ranks do not all stream their e2e inputs out of one socket's memory. Returns the node or None."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(index)
+        bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:
+        pass
+    return None
+
+
 def cpu_reference_rate(sample: int, repeats: int, threads: int):
     """queries/s of the reference's CPU `Evaluate` (oracle/_ref) on `sample` queries, best-of-median over repeats."""
     os.environ.setdefault("OMP_NUM_THREADS", str(threads))
@@ -161,6 +184,7 @@ def main():
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback; use --impl reference for the CPU arm)"
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None  # pinned e2e buffers then live next to this rank's GPU
     dev = f"cuda:{local}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -307,7 +331,8 @@ def main():
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "queries_per_gpu_per_step": n, "network": "64->5x(64,ReLU)->3, fp16 weights, fp32 TMEM accumulate",
-                   "l2_policy": "inputs (265 MB per step) exceed the 126 MB L2; no flush needed", "parallelism": f"index-range x{world}"},
+                   "l2_policy": "inputs (265 MB per step) exceed the 126 MB L2; no flush needed", "parallelism": f"index-range x{world}",
+                   "host_numa_node_rank0": numa},
         "e2e": {"value": world * n / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 128, "d2h_bytes_per_step": n * 6,
                 "ms_per_step": ms_e2e},
         "gpu_launches": K,  # one nrc_infer_kernel launch per step inside the timed region
