@@ -41,10 +41,6 @@ __device__ unsigned int g_nrc_trace_n[4];
 #endif
 #define NRC_TRACE_TAG(ev) ((uint32_t)(ev) << 24 | (uint32_t)l << 16 | (j & 0xffffu))
 
-#ifndef NRC_INFER_FLUSH_LAYER
-#define NRC_INFER_FLUSH_LAYER 0
-#endif
-
 namespace nrc {
 
 // Shared memory: weights (6 x 8 KB), two 16 KB input buffers per slot, barriers.
@@ -316,11 +312,7 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 		const uint64_t gi = (uint64_t)tile * NRC_TILE + row;
 		const bool valid = gi < n;
 		uint32_t b_lo = w_lo; // descriptor (low word) of W_l, advanced by one 8 KB matrix per layer
-#ifdef NRC_INFER_NO_UNROLL
-#pragma unroll 1
-#else
 #pragma unroll // layer index static: no per-layer branches, descriptors are immediates (70 -> 59.5 us at 1080p)
-#endif
 		for (int l = 0; l < NRC_LAYERS; ++l, b_lo += 8192 >> 4) {
 			// ---- issue layer l of this slot's tile
 			NRC_TRACE_EV(s, NRC_TRACE_TAG(1));
@@ -354,7 +346,7 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 				}
 				__syncwarp();
 			}
-			if (l == NRC_INFER_FLUSH_LAYER && pend) {
+			if (l == 0 && pend) {
 				write_result(p, pend_gi, pend_y0, pend_y1, pend_y2, pf);
 				pend = false;
 			}
@@ -391,10 +383,6 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 				pend = valid, pend_gi = gi;
 				pend_y0 = __half2float(__ushort_as_half((unsigned short)y[0])), pend_y1 = __half2float(__ushort_as_half((unsigned short)y[1]));
 				pend_y2 = __half2float(__ushort_as_half((unsigned short)y[2]));
-				if (NRC_INFER_FLUSH_LAYER < 0 && pend) {
-					write_result(p, pend_gi, pend_y0, pend_y1, pend_y2, pf);
-					pend = false;
-				}
 			}
 #else
 			if (l < NRC_HIDDEN_LAYERS) {
@@ -434,10 +422,6 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 				slot_sync(); // accumulator drained before the next tile's layer 0 overwrites it
 				pend = valid, pend_gi = gi;
 				pend_y0 = __uint_as_float(y[0]), pend_y1 = __uint_as_float(y[1]), pend_y2 = __uint_as_float(y[2]);
-				if (NRC_INFER_FLUSH_LAYER < 0 && pend) {
-					write_result(p, pend_gi, pend_y0, pend_y1, pend_y2, pf);
-					pend = false;
-				}
 			}
 #endif
 		}
