@@ -242,3 +242,66 @@ def test_train_frame_records_equals_four_batches(nrc, state):
     for k in ("weights", "use_weights", "optimizer_entries", "gradients"):
         assert np.array_equal(np.ascontiguousarray(a[k]).view(np.uint8), np.ascontiguousarray(b[k]).view(np.uint8)), k
     assert a["optimizer_state"]["t"] == 3
+
+
+def test_whole_frame_on_path_structured_records(nrc, oracle_mod):
+    """A frame as the reference's render graph runs it (src/rg/NRCRenderGraph.cpp:46-80) on records with the structure its
+    path tracer emits (vknrc_b200.synth.frame_records: screen queries for every pixel, train paths with suffix-scanned
+    bias / factor appended contiguously to random batches, a tail query per unfinished path whose answer is fed back into
+    that path's training targets, one batch overfull): nrc_infer (device count, use_weights) then nrc_train_frame (device
+    counts, clamped in place) against the oracle's unpack -> encode -> network -> scatter -> 4 x (gradient, Adam/EMA)."""
+    from vknrc_b200 import synth
+    sc = make_scene(61)
+    dsc = upload_scene(nrc, sc)
+    W, H, cap = 192, 96, 1024
+    n_prims, n_inst = sc.material_ids.shape[0], sc.transforms.shape[0]
+    fr = synth.frame_records(62, W, H, n_prims, n_inst, train_probability=0.25, batch_size=cap)
+    assert fr["train_counts"].max() > cap and fr["eval_count"] > W * H  # at least one batch overflows, tail queries exist
+    st = nrc.NrcState(0, (W, H), seed=5)
+    w32 = he_weights(63)
+    st.set_weights(w32)
+    rng = np.random.default_rng(64)
+    bf = rng.uniform(0, 1, (H, W, 4)).astype(np.float32)
+    gb = rng.uniform(0, 1, (H, W, 2)).astype(np.float32)
+    ev = fr["eval_records"]
+    n_ev = fr["eval_count"]
+    d_ev = dev(ev.view(np.uint8).reshape(-1))
+    d_bf, d_gb = dev(bf), dev(gb)
+    d_tr = [dev(t.view(np.uint8).reshape(-1)) for t in fr["train_records"]]
+    d_evc = torch.tensor([n_ev], dtype=torch.int32, device="cuda")
+    d_trc = [torch.tensor([int(c)], dtype=torch.int32, device="cuda") for c in fr["train_counts"]]
+    # ---- the frame
+    st.infer(d_ev, d_evc, dsc, d_bf, d_gb, W, d_tr, max_count=n_ev)
+    fed = [t.cpu().numpy().view(nrc.TRAIN_RECORD_DTYPE).copy() for t in d_tr]  # train records after the feedback
+    st.train_frame(d_tr, dsc, d_trc, max_count=cap)
+    got = st.download()
+    assert [int(c.item()) for c in d_trc] == [min(int(c), cap) for c in fr["train_counts"]]  # nrc_train_prepare.comp:17-19
+    # ---- oracle: inference + scatter (screen composite and feedback into the train targets)
+    pk = np.ascontiguousarray(ev["packed_input"]).view(np.uint32).reshape(n_ev, 4)
+    pred = oracle_mod.evaluate(w32.astype(np.float16), oracle_mod.encode(oracle_mod.unpack(sc, pk)), oracle_mod.ACC_FP32, clamp=True).astype(np.float32)
+    exp_bf = bf.copy()
+    exp_tr = [t.copy().view(np.float32).reshape(-1, 10) for t in fr["train_records"]]
+    oracle_mod.scatter(pred, np.ascontiguousarray(ev["dst"]), exp_bf, gb, W, exp_tr)
+    scale = np.abs(pred).max()
+    assert np.abs(d_bf.cpu().numpy() - exp_bf).max() <= 1e-2 * scale
+    for b in range(4):
+        g = fed[b].view(np.float32).reshape(-1, 10)
+        assert np.abs(g[:, :6] - exp_tr[b][:, :6]).max() <= 1e-2 * max(scale, np.abs(exp_tr[b][:, :3]).max())
+        assert np.array_equal(g[:, 6:].view(np.uint32), exp_tr[b][:, 6:].view(np.uint32))
+    # ---- oracle: the four training batches on the device's own fed-back targets and unpacked inputs (the gather is checked
+    # separately; its fp32 ulps are amplified by the top frequency octave), Adam / EMA chained, use_weights from batch 3
+    opt = oracle_mod.Optimizer(w32)
+    for b in range(4):
+        cnt = min(int(fr["train_counts"][b]), cap)
+        unp = nrc.unpack_inputs(d_tr[b][24:], dsc, stride_bytes=40, n=cnt).cpu().numpy()
+        tgt = np.ascontiguousarray(fed[b]["bias"][:cnt])
+        grad = oracle_mod.gradient(opt.weights, oracle_mod.encode(unp), tgt, oracle_mod.LOSS_RELATIVE_L2_LUMINANCE, 1.0, oracle_mod.ACC_FP32)
+        opt.step(grad, cnt, b == 3, False, batch_cap=cap)
+    # fp16 weights after four chained steps: the gradients agree to ~1e-5 of scale, Adam's first steps move every weight by
+    # about lr regardless of the gradient's size, so a sign flip of a near-zero gradient shows up as 2 lr = 4e-3
+    dw = np.abs(got["weights"].view(np.float16).astype(np.float32) - opt.weights.view(np.float16).astype(np.float32))
+    assert np.median(dw) <= 1e-4 and (dw > 5e-3).mean() <= 2e-3 and dw.max() <= 2e-2, (np.median(dw), (dw > 5e-3).mean(), dw.max())
+    s = got["optimizer_state"]
+    assert (s["t"], s["beta1_t"], s["beta2_t"], s["alpha_t"], s["alpha_t_1"]) == (
+        opt.state.t, opt.state.beta1_t, opt.state.beta2_t, opt.state.alpha_t, opt.state.alpha_t_1)
+    st.close()

@@ -72,3 +72,65 @@ def train_records(seed: int, n: int, n_prims: int, n_instances: int) -> np.ndarr
     r["bias"], r["factor"] = rng.uniform(0, 1, (n, 3)), rng.uniform(0, 1, (n, 3))
     r["packed_input"] = np.ascontiguousarray(random_packed_inputs(seed + 1, n, n_prims, n_instances)).view(TRAIN_RECORD_DTYPE["packed_input"]).reshape(n)
     return r
+
+
+MAX_BOUNCE = 8  # shader/src/path_tracer.comp:11
+CONST_LIGHT = 10.0  # kConstLight (path_tracer.comp:142): radiance of a ray that leaves the scene
+
+
+def frame_records(seed: int, width: int, height: int, n_prims: int, n_instances: int, train_probability: float = 0.03,
+                  batch_size: int = 16384, batch_count: int = 4, light_terminate_probability: float = 0.3) -> dict:
+    """One frame's record buffers with the STRUCTURE the reference's path tracer produces (path_tracer.comp:254-375, SURVEY
+    appendix B), from random hits instead of traced ones (the tracer itself is out of scope):
+      * every pixel appends one screen-destined NRCEvalRecord;
+      * with probability `train_probability` a whole subgroup (32 consecutive pixels of a row, path_tracer.comp:389-394) runs
+        extended "train" paths: `bounce` in [1, MAX_BOUNCE] vertices, per-vertex throughput colour and emitted light; the
+        suffix scan of :347-350 turns them into bias_i = radiance collected from vertex i on and factor_i = throughput from
+        vertex i to the path's tail; the `bounce` records go CONTIGUOUSLY into a random batch (atomic append, truncated at
+        the batch capacity while the count keeps growing, :343-351); unless the path left the scene, one more eval record
+        with dst = train(batch, first, last) asks the cache for the tail radiance, which nrc_inference.comp:60-72 adds to
+        every bias_i, i in [first, last], scaled by factor_i.
+    Returns eval_records, eval_count, train_records[batch_count] (capacity `batch_size` each) and the raw (unclamped) counts."""
+    rng = np.random.default_rng(seed)
+    n_pix = width * height
+    idx = np.arange(n_pix, dtype=np.uint32)
+    screen = np.zeros(n_pix, EVAL_RECORD_DTYPE)
+    screen["dst"] = ((idx % width) | ((idx // width) << 15)) << 1
+    screen["packed_input"] = np.ascontiguousarray(random_packed_inputs(seed + 1, n_pix, n_prims, n_instances)).view(EVAL_RECORD_DTYPE["packed_input"]).reshape(n_pix)
+    # which pixels run train paths: per subgroup of 32 consecutive pixels in a row
+    groups_per_row = (width + 31) // 32
+    train_group = rng.uniform(size=(height, groups_per_row)) < train_probability
+    train_pix = np.flatnonzero(np.repeat(train_group, 32, axis=1)[:, :width].reshape(-1))
+    trains = [np.zeros(batch_size, TRAIN_RECORD_DTYPE) for _ in range(batch_count)]
+    counts = np.zeros(batch_count, np.int64)
+    tails = []
+    n_paths = len(train_pix)
+    bounces = rng.integers(1, MAX_BOUNCE + 1, n_paths)
+    batches = np.minimum((rng.uniform(size=n_paths) * batch_count).astype(np.int64), batch_count - 1)
+    leaves = rng.uniform(size=n_paths) < light_terminate_probability
+    vertex_inputs = random_packed_inputs(seed + 2, int(bounces.sum()), n_prims, n_instances)
+    v0 = 0
+    for path in range(n_paths):
+        b, batch = int(bounces[path]), int(batches[path])
+        colors = rng.uniform(0.05, 0.95, (b, 3)).astype(np.float32)
+        lights = np.where(rng.uniform(size=(b, 1)) < 0.05, rng.uniform(0, 5, (b, 3)), 0.0).astype(np.float32)  # few emitters
+        if leaves[path]:
+            lights[b - 1] = CONST_LIGHT
+        for i in range(b - 2, -1, -1):  # path_tracer.comp:347-350 (fp32, same order)
+            lights[i] = lights[i] + colors[i] * lights[i + 1]
+            colors[i] = colors[i] * colors[i + 1]
+        first = int(counts[batch])
+        counts[batch] += b  # the atomic keeps counting past the capacity (:343-345)
+        if first < batch_size:
+            cnt = min(b, batch_size - first)
+            rec = trains[batch][first:first + cnt]
+            rec["bias"], rec["factor"] = lights[:cnt], colors[:cnt]
+            rec["packed_input"] = np.ascontiguousarray(vertex_inputs[v0:v0 + cnt]).view(TRAIN_RECORD_DTYPE["packed_input"]).reshape(cnt)
+            if not leaves[path]:
+                tail = np.zeros(1, EVAL_RECORD_DTYPE)
+                tail["dst"] = (((batch | (first << 2) | ((first + cnt - 1) << 16)) << 1) | 1) & 0xFFFFFFFF
+                tail["packed_input"] = np.ascontiguousarray(vertex_inputs[v0 + b - 1:v0 + b]).view(EVAL_RECORD_DTYPE["packed_input"]).reshape(1)
+                tails.append(tail)
+        v0 += b
+    ev = np.concatenate([screen] + tails) if tails else screen
+    return {"eval_records": ev, "eval_count": len(ev), "train_records": trains, "train_counts": counts, "train_paths": n_paths}
