@@ -521,3 +521,34 @@ def test_full_size_training_properties(nrc, oracle_mod):
                                oracle_mod.ACC_FP32)
     assert max(layer_rel_err(st.download()["gradients"][:nrc.WEIGHT_COUNT], gref)) <= GRAD_REL_TOL
     st.close()
+
+
+def test_training_calls_replay_correctly_from_a_cuda_graph(nrc, state):
+    """The library launches on the caller's stream and never synchronises, so a frame can be captured into a CUDA graph.
+    Nothing that changes from launch to launch (grid-barrier base, optimizer step count) may be baked into the launch
+    parameters: three replays of a captured nrc_train_frame must equal three direct calls bit for bit."""
+    w32 = he_weights(71)
+    n = 3000
+    recs = [dev(random_records(80 + b, n)) for b in range(4)]
+    tgts = [dev(np.random.default_rng(90 + b).uniform(0, 1, (n, 3)).astype(np.float32)) for b in range(4)]
+    state.set_weights(w32)
+    for _ in range(3):
+        state.train_frame_unpacked(recs, tgts)
+    direct = state.download()
+    state.set_weights(w32)
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        with torch.cuda.graph(g, stream=s):
+            state.train_frame_unpacked(recs, tgts)
+    torch.cuda.current_stream().wait_stream(s)
+    torch.cuda.synchronize()
+    state.set_weights(w32)  # (capture does not execute; start from the same state as the direct run)
+    for _ in range(3):
+        g.replay()
+    torch.cuda.synchronize()
+    replayed = state.download()
+    assert np.array_equal(direct["weights"].view(np.uint16), replayed["weights"].view(np.uint16))
+    assert np.array_equal(direct["optimizer_entries"].view(np.uint32), replayed["optimizer_entries"].view(np.uint32))
+    assert direct["optimizer_state"] == replayed["optimizer_state"] and replayed["optimizer_state"]["t"] == 12

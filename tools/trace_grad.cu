@@ -36,9 +36,7 @@ int main(int argc, char **argv) {
 	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 	for (int it = 0; it < 4; ++it) {
 		cudaEventRecord(e0);
-		uint32_t grid = 0;
-		cudaError_t le = nrc::launch_train(tp, tw, tw, 148, 0, &grid);
-		tp.grid_bar_base += grid * (2u * nb - 1u);
+		cudaError_t le = nrc::launch_train(tp, tw, tw, 148, 0);
 		cudaEventRecord(e1);
 		cudaError_t e = cudaDeviceSynchronize();
 		float ms; cudaEventElapsedTime(&ms, e0, e1); printf("train kernel (%d batch%s of %llu) %.1f us (%s / %s)\n", nb, nb > 1 ? "es" : "", (unsigned long long)n, ms * 1e3, cudaGetErrorString(le), cudaGetErrorString(e));

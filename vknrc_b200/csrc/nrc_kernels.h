@@ -93,7 +93,7 @@ struct AdamParams {
 #define NRC_MAX_RANKS 8
 struct CommParams {
 	uint32_t rank, world;           // world <= 1: no exchange
-	uint32_t epoch_base;            // batch b of this launch uses epoch epoch_base + b (never 0)
+	uint32_t *epoch_word;           // device word: epochs used so far; batch b of a launch uses epoch *epoch_word + 1 + b (never 0)
 	uint64_t *inbox[NRC_MAX_RANKS]; // comm buffer of every rank as mapped into this process (inbox[rank] = the local one)
 };
 constexpr size_t kCommDataWords = 2ull * NRC_MAX_RANKS * NRC_GRAD_STRIDE;
@@ -112,8 +112,7 @@ struct TrainParams {
 	uint32_t limit;        // number of leading elements to produce (20672 for a caller's dW, NRC_GRAD_STRIDE otherwise)
 	uint32_t batch_cap;    // d_count is clamped in place to this (nrc_train_prepare.comp:17-19)
 	AdamParams adam;       // use_weights / use_ema are taken from here when adam_mode == 2
-	uint32_t *grid_bar;    // monotonic arrival counter of the grid barrier (owned by the state, never reset)
-	uint32_t grid_bar_base; // its value before this launch (every launch adds grid * (2 * num_batches - 1))
+	uint32_t *grid_bar;    // {monotonic arrival counter of the grid barrier, its value before the next launch} (owned by the state)
 	CommParams comm;
 	uint32_t pool_tiles;   // activation tiles in shared memory (set by launch_train: 8, or 6 when no CTA has a second tile)
 };

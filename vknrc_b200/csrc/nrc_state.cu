@@ -148,7 +148,8 @@ int NrcState::CommInit(uint32_t rank, uint32_t world, cudaIpcMemHandle_t *out_ha
 	NRC_CUDA_TRY(cudaMemset(m_comm_local, 0, kCommBytes), sink);
 	NRC_CUDA_TRY(cudaDeviceSynchronize(), sink);
 	NRC_CUDA_TRY(cudaIpcGetMemHandle(out_handle, m_comm_local), sink);
-	m_comm_rank = rank, m_comm_world = world, m_comm_epoch = 0;
+	m_comm_rank = rank, m_comm_world = world;
+	NRC_CUDA_TRY(cudaMemset(m_sync_words + 4, 0, sizeof(uint32_t)), sink); // exchange epochs restart with the fresh (zeroed) inboxes
 	return NRC_OK;
 }
 int NrcState::CommConnect(const cudaIpcMemHandle_t *all_handles) {
@@ -208,8 +209,7 @@ int NrcState::upload_initial(const float *w) {
 	NRC_CUDA_TRY(cudaMemcpy(m_use_weights, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice), sink);
 	NRC_CUDA_TRY(cudaMemcpy(m_optimizer_entries, e.data(), e.size() * sizeof(NrcOptimizerEntry), cudaMemcpyHostToDevice), sink);
 	NRC_CUDA_TRY(cudaMemcpy(m_optimizer_state, &st, sizeof(st), cudaMemcpyHostToDevice), sink);
-	NRC_CUDA_TRY(cudaMemset(m_sync_words, 0, 8 * sizeof(uint32_t)), sink);
-	m_grid_bar_count = 0;
+	NRC_CUDA_TRY(cudaMemset(m_sync_words, 0, 4 * sizeof(uint32_t)), sink); // (not [4]: exchange epochs only restart with fresh inboxes)
 	return NRC_OK;
 }
 
@@ -319,20 +319,17 @@ int NrcState::Train(TrainParams tp, const void *encoded_inputs, const __half *we
 	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
 	for (uint32_t b = 0; b < tp.num_batches; ++b)
 		tp.batch[b].partials = m_partials;
-	tp.grid_bar = m_sync_words + 2, tp.grid_bar_base = m_grid_bar_count;
+	tp.grid_bar = m_sync_words + 2;
 	tp.adam.gradients = tp.gradients, tp.adam.entries = m_optimizer_entries, tp.adam.opt_state = m_optimizer_state;
 	tp.adam.done_counter = m_sync_words, tp.adam.weights = m_weights, tp.adam.use_weights = m_use_weights;
 	tp.adam.use_ema = m_use_ema_weights ? 1 : 0;
 	tp.comm = CommParams{};
 	if (m_comm_connected && m_comm_world > 1 && !tp.accumulate) { // (the handle-less test-harness calls never exchange)
-		tp.comm.rank = m_comm_rank, tp.comm.world = m_comm_world, tp.comm.epoch_base = m_comm_epoch + 1;
+		tp.comm.rank = m_comm_rank, tp.comm.world = m_comm_world, tp.comm.epoch_word = m_sync_words + 4;
 		for (uint32_t r = 0; r < m_comm_world; ++r)
 			tp.comm.inbox[r] = m_comm_inbox[r];
-		m_comm_epoch += tp.num_batches;
 	}
-	uint32_t grid = 0;
-	NRC_CUDA_TRY(launch_train(tp, tm_w, tm_in, m_sms, stream, &grid), sink);
-	m_grid_bar_count += grid * (2u * tp.num_batches - 1u); // what the launch adds to the grid-barrier counter
+	NRC_CUDA_TRY(launch_train(tp, tm_w, tm_in, m_sms, stream), sink);
 	return NRC_OK;
 }
 

@@ -102,8 +102,9 @@ private:
 	NrcOptimizerState *m_optimizer_state{nullptr};
 	NrcOptimizerEntry *m_optimizer_entries{nullptr};
 	float *m_gradients{nullptr}, *m_partials{nullptr};
-	uint32_t *m_sync_words{nullptr}; // [0] optimizer "last CTA" counter, [2] grid-barrier arrival counter (monotonic)
-	uint32_t m_grid_bar_count{0};    // host mirror of [2]: what it will read once every launch enqueued so far has run
+	uint32_t *m_sync_words{nullptr}; // [0] optimizer "last CTA" counter, [2] grid-barrier arrival counter (monotonic), [3] its
+	                                 // base for the next launch, [4] multi-GPU exchange epochs used so far - all device-resident,
+	                                 // so a captured CUDA graph of the training calls replays correctly
 	float *m_prediction_capture{nullptr};
 
 	// host-buffer path: device staging (grown on demand), copy-in / copy-out streams, per-chunk events
@@ -115,7 +116,7 @@ private:
 
 	uint64_t *m_comm_local{nullptr};
 	uint64_t *m_comm_inbox[NRC_MAX_RANKS]{};
-	uint32_t m_comm_rank{0}, m_comm_world{1}, m_comm_epoch{0};
+	uint32_t m_comm_rank{0}, m_comm_world{1};
 	bool m_comm_connected{false};
 
 	uint32_t m_seed{0};

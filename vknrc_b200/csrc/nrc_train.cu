@@ -125,8 +125,10 @@ __device__ __forceinline__ void publish_state_if_last(const AdamParams &a, const
 // ------------------------------------------------------------------------------------------------------------------
 // Grid barrier. All CTAs of the (cooperative) launch are co-resident. ONE monotonically increasing arrival counter,
 // never reset: barrier k of a launch is passed when the counter reaches base + (k + 1) * gridDim.x, where `base` is the
-// counter's value before the launch (tracked by the host object: every launch adds gridDim.x * #barriers; wrap-around
-// is harmless, the comparison is on the signed difference). An arrival is one fire-and-forget red; the waiters poll the
+// counter's value before the launch. The base lives in device memory next to the counter (bar[1]): every CTA reads it
+// when the kernel starts and CTA 0 stores the final value after the launch's last barrier - by then every CTA has read
+// the old one - so nothing about the barrier is baked into the launch parameters and a captured CUDA graph replays
+// correctly. Wrap-around is harmless, the comparison is on the signed difference. An arrival is one fire-and-forget red; the waiters poll the
 // counter itself, so a barrier costs fence + one-way red + one load round trip (1800 cycles; the earlier generation-word
 // scheme - load generation, atomic with return, last arriver stores, the others poll - measured 3050).
 // Release: the CTA barrier orders every thread's global writes before thread 0's __threadfence + arrival. Acquire:
@@ -316,7 +318,9 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		arrive_ready(af_ready);
 	}
 	uint32_t w_reloads = 0; // weight re-stagings by the epilogue warps so far (w_ready phase)
-	uint32_t bar_target = tp.grid_bar_base; // (meaningful in thread 0 only)
+	uint32_t bar_target = *(volatile const uint32_t *)(tp.grid_bar + 1); // (meaningful in thread 0 only)
+	// multi-GPU: the epoch of this launch's first exchange, also device-resident (advanced by CTA 0 below)
+	const uint32_t epoch_base = tp.comm.world > 1 ? *(volatile const uint32_t *)tp.comm.epoch_word + 1u : 0u;
 
 #pragma unroll 1
 	for (uint32_t b = 0; b < tp.num_batches; ++b) {
@@ -691,6 +695,12 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		bool publish_pending = false;
 		grid_sync<false>(tp.grid_bar, bar_target);
 		NRC_GTRACE(9);
+		if (blockIdx.x == 0 && threadIdx.x == 0) { // (every CTA has passed this launch's first barrier: the old values are read)
+			if (b + 1 == tp.num_batches)
+				tp.grid_bar[1] = bar_target; // the launch's last barrier: publish the counter's final value as the next base
+			if (b == 0 && tp.comm.world > 1)
+				*tp.comm.epoch_word = epoch_base - 1u + tp.num_batches;
+		}
 		{
 			const uint32_t num_partials = gridDim.x;
 			// the batch's record count: integers < 2^24, so any summation order is exact (the load is issued here, its
@@ -710,7 +720,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 				old.t = os->t, old.beta1_t = os->beta1_t, old.beta2_t = os->beta2_t, old.alpha_t = os->alpha_t, old.alpha_t_1 = os->alpha_t_1;
 				st = advance_state(old);
 			}
-			const uint32_t world = tp.comm.world, me = tp.comm.rank, epoch = tp.comm.epoch_base + b, parity = epoch & 1u;
+			const uint32_t world = tp.comm.world, me = tp.comm.rank, epoch = epoch_base + b, parity = epoch & 1u;
 			// The 20 736 floats are cut in blocks of 64; CTA c owns blocks c, c + grid, ... and handles up to three of them
 			// per round. Per block: 16 threads x float4 cover the 64 floats of one partial, 16 groups of them take the
 			// partials g, g + 16, g + 32, ... (all loads in flight at once), and the 16 group sums are combined by a
