@@ -42,3 +42,21 @@ for e in range(14, 23, 2):
     te = timed(lambda: st.gradient_encoded(x, t16), steps)
     tr = timed(lambda: st.train_batch_unpacked(rec, tgt, write_use_weights=True), steps)
     print(f"2^{e:<8} {te * 1e6:12.1f} {n * 115840 / te / 1e12:9.1f} {tr * 1e6:16.1f} {n / tr:12.3e} {n * 115840 / tr / 1e12:9.1f}")
+# BASELINE config 2: learn-an-image (test/mlp_learning_an_image): 16384 random-uv samples per SGD step, 640x640 inference per frame
+img = torch.randint(0, 256, (512, 512, 4), dtype=torch.uint8, device="cuda", generator=g)
+st2 = nrc.NrcState(0, (640, 640), seed=2)
+out = torch.empty((640, 640, 4), dtype=torch.uint8, device="cuda")
+seed = [0]
+
+
+def image_frame():
+    seed[0] += 1
+    st2.image_train_step(img, 1234 + seed[0], 99 + 7 * seed[0])
+    st2.image_infer(640, out)
+
+
+ts = timed(lambda: st2.image_train_step(img, 5, 6), 50)
+ti = timed(lambda: st2.image_infer(640, out), 50)
+tf = timed(image_frame, 50)
+print("learn-an-image (config 2)")
+print(f"train step (16384 samples, SGD) {ts * 1e6:7.1f} us | inference 640x640 {ti * 1e6:7.1f} us ({409600 / ti:.3e} queries/s) | frame (step + inference) {tf * 1e6:7.1f} us = {1 / tf:7.0f} frames/s")
