@@ -180,15 +180,36 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 	// warp index through a shuffle: the compiler then knows it is warp-uniform and keeps everything derived from it (slot,
 	// TMEM addresses, UMMA descriptors) in uniform registers - no R2UR chains in front of the tcgen05 instructions
 	const uint32_t warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0), lane = threadIdx.x & 31;
+#ifndef NRC_INFER_NO_PDL
+	// Programmatic dependent launch: the next kernel of the stream may place its CTAs on an SM the moment this kernel's
+	// CTA there exits (every CTA needs the whole TMEM and most of the shared memory, so nothing overlaps - what goes away
+	// is the grid-completion -> launch latency between back-to-back launches: -1.0 .. -1.9 us per 1080p launch).
+	asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+#endif
+	// prologue that depends on nothing an earlier kernel wrote: barriers, TMEM
+	if (threadIdx.x == 0) {
+		mbar_init(w_full, 1);
+		for (int i = 0; i < NT; ++i) {
+			mbar_init(d_full + i, 1);
+			for (int b = 0; b < 2; ++b)
+				mbar_init(in_full + 2 * i + b, NP ? 4 : 1), mbar_init(in_free + 2 * i + b, 1);
+		}
+		fence_mbar_init();
+		tma_prefetch_desc(&tm_w);
+	}
+	if (warp == 0)
+		tmem_alloc(tmem_slot, 512);
+#ifndef NRC_INFER_NO_PDL
+	// everything the previous kernel of the stream wrote (records, counts, weights, scene tables) is read after this point
+	asm volatile("griddepcontrol.wait;" ::: "memory");
+#endif
 	uint64_t n = p.n;
 	if (p.d_count) { // device-resident count, like the reference's indirect dispatch (nrc_indirect.comp:10)
 		const uint64_t c = *p.d_count;
 		n = c < n ? c : n;
 	}
 	const uint32_t ntiles = (uint32_t)((n + NRC_TILE - 1) / NRC_TILE);
-	if (blockIdx.x >= ntiles)
-		return;
-	const uint32_t my_tiles = (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x;
+	const uint32_t my_tiles = blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
 
 	const float *lut = (const float *)(smem + L::kLutOff);
 	const NrcTexture *textures = p.scene.textures;
@@ -202,23 +223,16 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 			textures = tsm;
 		}
 	}
-	if (threadIdx.x == 0) {
-		mbar_init(w_full, 1);
-		for (int i = 0; i < NT; ++i) {
-			mbar_init(d_full + i, 1);
-			for (int b = 0; b < 2; ++b)
-				mbar_init(in_full + 2 * i + b, NP ? 4 : 1), mbar_init(in_free + 2 * i + b, 1);
-		}
-		fence_mbar_init();
-	}
-	if (warp == 0)
-		tmem_alloc(tmem_slot, 512);
 	tc_fence_before();
 	__syncthreads();
 	tc_fence_after();
 	const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+	if (my_tiles == 0) { // (the device-resident count left this CTA without work)
+		if (warp == 0)
+			tmem_dealloc(tmem, 512);
+		return;
+	}
 	if (threadIdx.x == 0) { // all six weight matrices, once per CTA
-		tma_prefetch_desc(&tm_w);
 		mbar_arrive_expect_tx(w_full, L::kWeightBytes);
 		for (int l = 0; l < NRC_LAYERS; ++l)
 			tma_load_2d(w_sm + l * 8192, &tm_w, 0, l * 64, w_full);
@@ -454,8 +468,18 @@ template <int NT, int NP, int IN_MODE> static cudaError_t launch(const InferPara
 	}
 	const uint64_t ntiles = (p.n + NRC_TILE - 1) / NRC_TILE;
 	const uint32_t grid = (uint32_t)(ntiles < (uint64_t)sms ? ntiles : (uint64_t)sms);
+#ifdef NRC_INFER_NO_PDL
 	kern<<<grid, (NT * 4 + NP) * 32, smem_bytes, stream>>>(p, tm_w, tm_in);
 	return cudaGetLastError();
+#else
+	cudaLaunchConfig_t cfg{};
+	cfg.gridDim = dim3(grid), cfg.blockDim = dim3((NT * 4 + NP) * 32), cfg.dynamicSmemBytes = smem_bytes, cfg.stream = stream;
+	cudaLaunchAttribute attr[1];
+	attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization; // see griddepcontrol.* at the top of the kernel
+	attr[0].val.programmaticStreamSerializationAllowed = 1;
+	cfg.attrs = attr, cfg.numAttrs = 1;
+	return cudaLaunchKernelEx(&cfg, kern, p, tm_w, tm_in);
+#endif
 }
 
 // Stand-alone UnpackNRCInput (NRCRecord.glsl:98-125): [n] PackedNRCInput -> [n][14] fp32. The fused kernels above never
