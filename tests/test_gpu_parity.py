@@ -539,9 +539,12 @@ def test_training_calls_replay_correctly_from_a_cuda_graph(nrc, state):
     s = torch.cuda.Stream()
     s.wait_stream(torch.cuda.current_stream())
     g = torch.cuda.CUDAGraph()
+    x = torch.rand((5000, 64), device="cuda").half()
+    y = torch.zeros((5000, 3), device="cuda", dtype=torch.float16)
     with torch.cuda.stream(s):
         with torch.cuda.graph(g, stream=s):
             state.train_frame_unpacked(recs, tgts)
+            state.infer_encoded(x, y, clamp=True)  # (launched with programmatic stream serialization: must capture too)
     torch.cuda.current_stream().wait_stream(s)
     torch.cuda.synchronize()
     state.set_weights(w32)  # (capture does not execute; start from the same state as the direct run)
@@ -552,3 +555,4 @@ def test_training_calls_replay_correctly_from_a_cuda_graph(nrc, state):
     assert np.array_equal(direct["weights"].view(np.uint16), replayed["weights"].view(np.uint16))
     assert np.array_equal(direct["optimizer_entries"].view(np.uint32), replayed["optimizer_entries"].view(np.uint32))
     assert direct["optimizer_state"] == replayed["optimizer_state"] and replayed["optimizer_state"]["t"] == 12
+    assert torch.equal(y, state.infer_encoded(x, clamp=True))  # the captured inference ran on the weights of the third replay
