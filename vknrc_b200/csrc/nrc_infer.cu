@@ -18,7 +18,7 @@
 //     fused into the first layer, and the gather / encode latency never sits in a slot's MMA -> epilogue chain.
 // Hand-offs: a 128-thread named barrier inside the slot (operand stored / accumulator drained -> issuer), the
 // mbarriers d_full[slot] (tcgen05.commit -> epilogue), in_full[slot][2] (TMA or 4 producer warps -> layer-0 MMA) and
-// in_free[slot][2] (layer 0 done -> producers).
+// in_free[slot][2] (a use counter per buffer: layer 0 done -> producers).
 #include "nrc_kernels.h"
 #include "nrc_encode.cuh"
 #include "nrc_unpack.cuh"
@@ -170,7 +170,8 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 	uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	uint8_t *w_sm = smem;
 	uint64_t *bars = (uint64_t *)(smem + L::kBarOff);
-	uint64_t *w_full = bars, *d_full = bars + 1, *in_full = d_full + NT, *in_free = in_full + 2 * NT; // in_full / in_free [slot][2]
+	uint64_t *w_full = bars, *d_full = bars + 1, *in_full = d_full + NT; // in_full[slot][2]
+	volatile uint32_t *in_free = (volatile uint32_t *)(in_full + 2 * NT); // in_free[slot][2]: uses of the buffer the slot is done with
 	uint32_t *tmem_slot = (uint32_t *)(in_free + 2 * NT);
 #ifdef NRC_TRACE
 	uint2 *trace_sm = (uint2 *)(smem + L::kTraceOff);
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 		for (int i = 0; i < NT; ++i) {
 			mbar_init(d_full + i, 1);
 			for (int b = 0; b < 2; ++b)
-				mbar_init(in_full + 2 * i + b, NP ? 4 : 1), mbar_init(in_free + 2 * i + b, 1);
+				mbar_init(in_full + 2 * i + b, NP ? 4 : 1), in_free[2 * i + b] = 0u;
 		}
 		fence_mbar_init();
 		tma_prefetch_desc(&tm_w);
@@ -241,11 +242,10 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 	if (NP > 0 && warp >= NT * 4) {
 		// ------------------------------------------------------------------------------------------ producer warps
 		// unit u = quarter (u & 3) of the CTA's tile g = u >> 2, which slot g % NT runs as its (g / NT)-th tile from
-		// buffer (g / NT) & 1. Units repeat their (slot, buffer, quarter) with period 8 NT; a producer warp owns a fixed
-		// set of those combinations (NP divides 8 NT), so it meets the uses of one buffer in order and a parity wait on
-		// in_free can never be a whole phase behind. The raw record of the warp's next unit is fetched before the
-		// current one is processed.
-		static_assert((8 * NT) % (NP ? NP : 1) == 0, "the producer warps must tile the (slot, buffer, quarter) combinations evenly");
+		// buffer (g / NT) & 1. A buffer is handed back through a use COUNTER in shared memory (the slot's issuing thread
+		// stores "uses finished"; the producer of use m waits for the counter to reach m): unlike a parity wait this cannot
+		// miss a phase, so any number of producer warps may take the units round-robin. The raw record of the warp's next
+		// unit is fetched before the current one is processed.
 		const uint32_t pw = warp - NT * 4, units = 4 * my_tiles;
 		auto unit_gi = [&](uint32_t u) { return (uint64_t)(blockIdx.x + (u >> 2) * gridDim.x) * NRC_TILE + (u & 3u) * 32 + lane; };
 		RawInput<IN_MODE> raw, raw_next;
@@ -259,8 +259,14 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 				load_raw<IN_MODE>(p, unit_gi(u + NP), unit_gi(u + NP) < n, raw_next);
 			uint32_t o[32];
 			encode_raw<IN_MODE>(p, gi, gi < n, raw, o, lut, textures);
-			if (it >= 2) // the slot has finished layer 0 of the tile that used this buffer before
-				mbar_wait(in_free + 2 * s + b, ((it >> 1) - 1) & 1);
+			if (it >= 2) { // the slot has finished layer 0 of the tile that used this buffer before
+				for (uint32_t spins = 0; in_free[2 * s + b] < (it >> 1); ++spins) {
+					if (spins > (1u << 22))
+						__trap(); // a protocol bug must not hang the GPU
+					__nanosleep(NRC_INFER_FREE_BACKOFF);
+				}
+				__threadfence_block();
+			}
 			uint8_t *dst = smem + L::kInOff + (s * 2 + b) * 16384 + row * 128;
 #pragma unroll
 			for (int c = 0; c < 8; ++c)
@@ -281,7 +287,7 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 	const uint32_t d_col = tmem + s * 96, a_col = d_col + 64;             // issuer's view (lane 0)
 	const uint32_t d_t = tmem_addr(tmem, q * 32, s * 96), a_t = d_t + 64; // this warp's 32 lanes
 	uint8_t *in_sm = smem + L::kInOff + s * 2 * 16384;
-	uint64_t *my_in_full = in_full + 2 * s, *my_in_free = in_free + 2 * s, *my_d_full = d_full + s;
+	uint64_t *my_in_full = in_full + 2 * s, *my_d_full = d_full + s;
 #ifdef NRC_INFER_F16ACC
 	constexpr uint32_t idesc64 = make_idesc_f16_f16(128, 64, false, false);
 	constexpr uint32_t idesc16 = make_idesc_f16_f16(128, 16, false, false);
@@ -353,7 +359,7 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 							if (it + 2 < slot_tiles)
 								load_input_tile(it + 2);
 						} else {
-							mbar_arrive(my_in_free + (it & 1));
+							in_free[2 * s + (it & 1)] = (it >> 1) + 1; // (this thread observed layer 0's completion one layer ago)
 						}
 					}
 					NRC_TRACE_EV(s, NRC_TRACE_TAG(0));
@@ -540,7 +546,7 @@ cudaError_t launch_infer(const InferParams &p, const CUtensorMap &tm_w, const CU
 	case NRC_IN_IMAGE_GRID:
 		return launch<NTP, NP, NRC_IN_IMAGE_GRID>(p, tm_w, tm_in, sms, stream);
 	case NRC_IN_PACKED:
-		return launch<NTP, NP, NRC_IN_PACKED>(p, tm_w, tm_in, sms, stream);
+		return launch<NRC_INFER_SLOTS_PACKED, NRC_INFER_PRODUCER_WARPS_PACKED, NRC_IN_PACKED>(p, tm_w, tm_in, sms, stream);
 	}
 	return cudaErrorInvalidValue;
 }

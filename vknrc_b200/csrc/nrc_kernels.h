@@ -10,14 +10,25 @@
 #ifndef NRC_INFER_SLOTS
 #define NRC_INFER_SLOTS 5 // 128-sample tiles in flight per SM: 5 x (64 accumulator + 32 operand) = 480 of 512 TMEM columns
 #endif
-// record input modes: slots + producer warps (unpack / encode ahead of the slots) share the 32 warps of a CTA
-// (measured at 1080p, unpacked / packed+scatter: 4+16: 94 / 207 us, 4+8: 102 / 259 us, 5+10: 107 / 278 us; before the
-// producer warps existed, 5 slots doing their own unpack + encode: 113 / 241 us)
+// record input modes: slots + producer warps (unpack / encode ahead of the slots) share the 32 warps of a CTA.
+// Measured at 1080p (14-float records): 5 slots + 12 producers 81.0 us, 4 + 16: 83.6, 4 + 12: 82.8, 4 + 14: 83.8; before the
+// producer warps existed (5 slots doing their own unpack + encode, old encoder): 113 us.
 #ifndef NRC_INFER_SLOTS_REC
-#define NRC_INFER_SLOTS_REC 4
+#define NRC_INFER_SLOTS_REC 5
 #endif
 #ifndef NRC_INFER_PRODUCER_WARPS
-#define NRC_INFER_PRODUCER_WARPS 16 // must divide 8 * NRC_INFER_SLOTS_REC
+#define NRC_INFER_PRODUCER_WARPS 12
+#endif
+#ifndef NRC_INFER_FREE_BACKOFF
+#define NRC_INFER_FREE_BACKOFF 200 // ns between polls of a buffer's use counter
+#endif
+// packed records (scene gather): the producers are latency-bound, so they get more of the CTA's 32 warps
+// (nrc_infer at 1080p: 3 slots + 20 producers 133 us, 3 + 16: 141, 4 + 16: 143, 2 + 24: 151)
+#ifndef NRC_INFER_SLOTS_PACKED
+#define NRC_INFER_SLOTS_PACKED 3
+#endif
+#ifndef NRC_INFER_PRODUCER_WARPS_PACKED
+#define NRC_INFER_PRODUCER_WARPS_PACKED 20
 #endif
 
 namespace nrc {
