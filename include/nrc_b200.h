@@ -181,6 +181,27 @@ int nrc_image_train_step(nrc_handle_t h, const void *d_image_rgba8, uint32_t ima
                          uint32_t seed_y, uint32_t batch, float lr, void *stream);
 int nrc_image_infer(nrc_handle_t h, void *d_out_rgba8, uint32_t width, void *stream);
 
+/* ---- Vulkan interop (optional) ----
+ * The reference owns every buffer on this path as a VkBuffer / VkImage: the persistent MLP buffers in VkNRCState
+ * (src/VkNRCState.cpp:59-88), the per-frame eval / train record, count and screen-image resources in the render graph
+ * (src/rg/NRCRenderGraph.cpp:139-175). A renderer that keeps allocating them in Vulkan exports the VkDeviceMemory as an
+ * opaque fd (VK_KHR_external_memory_fd, VK_EXTERNAL_MEMORY_HANDLE_TYPE_OPAQUE_FD_BIT) and imports it here; the mapped
+ * device pointer is what the d_* arguments above take. Queue ordering (the render graph's barriers between
+ * path_tracer.comp, the NN passes and screen.frag) becomes a timeline semaphore exported with
+ * VK_KHR_external_semaphore_fd: wait(value) on the library's stream before nrc_infer / nrc_train_frame, signal(value+1)
+ * after. A successfully imported fd belongs to the CUDA driver (do not close it). Mapped pointers are released with
+ * cudaFree before nrc_external_memory_release. NOT EXECUTED in this repo's environment (no Vulkan loader / ICD): only the
+ * argument and error paths are tested. */
+typedef struct nrc_external_memory_t *nrc_external_memory_handle_t;
+typedef struct nrc_external_semaphore_t *nrc_external_semaphore_handle_t;
+int nrc_import_vulkan_memory_fd(int device, int fd, uint64_t allocation_size, int dedicated, nrc_external_memory_handle_t *out);
+int nrc_external_memory_map_buffer(nrc_external_memory_handle_t m, uint64_t offset, uint64_t size, void **d_ptr);
+int nrc_external_memory_release(nrc_external_memory_handle_t m);
+int nrc_import_vulkan_timeline_semaphore_fd(int device, int fd, nrc_external_semaphore_handle_t *out);
+int nrc_external_semaphore_wait(nrc_external_semaphore_handle_t s, uint64_t value, void *stream);
+int nrc_external_semaphore_signal(nrc_external_semaphore_handle_t s, uint64_t value, void *stream);
+int nrc_external_semaphore_release(nrc_external_semaphore_handle_t s);
+
 #ifdef __cplusplus
 }
 #endif

@@ -150,6 +150,13 @@ SIGNATURES = {
     "nrc_scene_prim_table_bytes": (C.c_uint64, [C.c_uint32]),
     "nrc_scene_build_prim_table": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "nrc_image_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
+    "nrc_import_vulkan_memory_fd": (C.c_int, [C.c_int, C.c_int, C.c_uint64, C.c_int, C.POINTER(C.c_void_p)]),
+    "nrc_external_memory_map_buffer": (C.c_int, [C.c_void_p, C.c_uint64, C.c_uint64, C.POINTER(C.c_void_p)]),
+    "nrc_external_memory_release": (C.c_int, [C.c_void_p]),
+    "nrc_import_vulkan_timeline_semaphore_fd": (C.c_int, [C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "nrc_external_semaphore_wait": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "nrc_external_semaphore_signal": (C.c_int, [C.c_void_p, C.c_uint64, C.c_void_p]),
+    "nrc_external_semaphore_release": (C.c_int, [C.c_void_p]),
 }
 
 

@@ -20,6 +20,7 @@
 // mbarriers d_full[slot] (tcgen05.commit -> epilogue), in_full[slot][2] (TMA or 4 producer warps -> layer-0 MMA) and
 // in_free[slot][2] (a use counter per buffer: layer 0 done -> producers).
 #include "nrc_kernels.h"
+#include <atomic>
 #include "nrc_encode.cuh"
 #include "nrc_unpack.cuh"
 
@@ -465,12 +466,16 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 template <int NT, int NP, int IN_MODE> static cudaError_t launch(const InferParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream) {
 	auto kern = nrc_infer_kernel<NT, NP, IN_MODE>;
 	constexpr uint32_t smem_bytes = InferSmem<NT, IN_MODE>::kBytes;
-	static bool configured = false;
-	if (!configured) {
+	static std::atomic<uint64_t> configured{0}; // function attributes are per device: one bit per device ordinal
+	int dev = 0;
+	if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess)
+		return e;
+	const uint64_t dev_bit = 1ull << (dev & 63);
+	if (!(configured.load(std::memory_order_acquire) & dev_bit)) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
 		if (e != cudaSuccess)
 			return e;
-		configured = true;
+		configured.fetch_or(dev_bit, std::memory_order_release);
 	}
 	const uint64_t ntiles = (p.n + NRC_TILE - 1) / NRC_TILE;
 	const uint32_t grid = (uint32_t)(ntiles < (uint64_t)sms ? ntiles : (uint64_t)sms);

@@ -774,4 +774,115 @@ int nrc_image_infer(nrc_handle_t h, void *d_out_rgba8, uint32_t width, void *str
 	return h->state.Infer(p, nullptr, h->state.GetWeightBuffer(), (cudaStream_t)stream);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Vulkan interop. The reference allocates the record / count / weight / image buffers as VkBuffers /
+// VkImages (src/rg/NRCRenderGraph.cpp:139-175, src/VkNRCState.cpp:59-88); a renderer that keeps doing so exports each
+// VkDeviceMemory as an opaque fd (VK_KHR_external_memory_fd) and its timeline semaphore (VK_KHR_external_semaphore_fd)
+// and hands the fds over here. On success the fd is owned by the CUDA driver (do not close it), as CUDA specifies.
+// ------------------------------------------------------------------------------------------------------------------
+struct nrc_external_memory_t {
+	int device;
+	cudaExternalMemory_t mem;
+	uint64_t size;
+};
+struct nrc_external_semaphore_t {
+	int device;
+	cudaExternalSemaphore_t sem;
+};
+static int cuda_fail(const char *where, cudaError_t e) {
+	cudaGetLastError(); // (do not leave the error sticky for the caller's next runtime call)
+	return set_error(e == cudaErrorMemoryAllocation ? NRC_ERR_OUT_OF_MEMORY : NRC_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString(e));
+}
+
+int nrc_import_vulkan_memory_fd(int device, int fd, uint64_t allocation_size, int dedicated, nrc_external_memory_handle_t *out) {
+	NRC_REQUIRE(out, "nrc_import_vulkan_memory_fd: null output");
+	*out = nullptr;
+	NRC_REQUIRE(fd >= 0 && allocation_size > 0, "nrc_import_vulkan_memory_fd: bad fd or size");
+	if (cudaError_t e = cudaSetDevice(device); e != cudaSuccess)
+		return cuda_fail("nrc_import_vulkan_memory_fd: cudaSetDevice", e);
+	cudaExternalMemoryHandleDesc d{};
+	d.type = cudaExternalMemoryHandleTypeOpaqueFd, d.handle.fd = fd, d.size = allocation_size;
+	d.flags = dedicated ? cudaExternalMemoryDedicated : 0; // VkMemoryDedicatedAllocateInfo allocations must say so
+	nrc_external_memory_t *m = new (std::nothrow) nrc_external_memory_t{device, nullptr, allocation_size};
+	if (!m)
+		return set_error(NRC_ERR_OUT_OF_MEMORY, "nrc_import_vulkan_memory_fd: host allocation failed");
+	if (cudaError_t e = cudaImportExternalMemory(&m->mem, &d); e != cudaSuccess) {
+		delete m;
+		return cuda_fail("cudaImportExternalMemory", e);
+	}
+	*out = m;
+	return NRC_OK;
+}
+
+int nrc_external_memory_map_buffer(nrc_external_memory_handle_t m, uint64_t offset, uint64_t size, void **d_ptr) {
+	NRC_REQUIRE(m && d_ptr, "nrc_external_memory_map_buffer: null argument");
+	*d_ptr = nullptr;
+	NRC_REQUIRE(size > 0 && offset <= m->size && size <= m->size - offset, "nrc_external_memory_map_buffer: range outside the allocation");
+	if (cudaError_t e = cudaSetDevice(m->device); e != cudaSuccess)
+		return cuda_fail("nrc_external_memory_map_buffer: cudaSetDevice", e);
+	cudaExternalMemoryBufferDesc b{};
+	b.offset = offset, b.size = size;
+	if (cudaError_t e = cudaExternalMemoryGetMappedBuffer(d_ptr, m->mem, &b); e != cudaSuccess)
+		return cuda_fail("cudaExternalMemoryGetMappedBuffer", e);
+	return NRC_OK;
+}
+
+// every pointer mapped from `m` must have been cudaFree'd by the caller before (CUDA's rule for mapped buffers)
+int nrc_external_memory_release(nrc_external_memory_handle_t m) {
+	if (!m)
+		return NRC_OK;
+	cudaSetDevice(m->device);
+	const cudaError_t e = cudaDestroyExternalMemory(m->mem);
+	delete m;
+	return e == cudaSuccess ? NRC_OK : cuda_fail("cudaDestroyExternalMemory", e);
+}
+
+int nrc_import_vulkan_timeline_semaphore_fd(int device, int fd, nrc_external_semaphore_handle_t *out) {
+	NRC_REQUIRE(out, "nrc_import_vulkan_timeline_semaphore_fd: null output");
+	*out = nullptr;
+	NRC_REQUIRE(fd >= 0, "nrc_import_vulkan_timeline_semaphore_fd: bad fd");
+	if (cudaError_t e = cudaSetDevice(device); e != cudaSuccess)
+		return cuda_fail("nrc_import_vulkan_timeline_semaphore_fd: cudaSetDevice", e);
+	cudaExternalSemaphoreHandleDesc d{};
+	d.type = cudaExternalSemaphoreHandleTypeTimelineSemaphoreFd, d.handle.fd = fd;
+	nrc_external_semaphore_t *s = new (std::nothrow) nrc_external_semaphore_t{device, nullptr};
+	if (!s)
+		return set_error(NRC_ERR_OUT_OF_MEMORY, "nrc_import_vulkan_timeline_semaphore_fd: host allocation failed");
+	if (cudaError_t e = cudaImportExternalSemaphore(&s->sem, &d); e != cudaSuccess) {
+		delete s;
+		return cuda_fail("cudaImportExternalSemaphore", e);
+	}
+	*out = s;
+	return NRC_OK;
+}
+
+// the renderer signals `value` after the path tracer wrote the frame's records (src/rg/NRCRenderGraph.cpp:60-70 order)
+int nrc_external_semaphore_wait(nrc_external_semaphore_handle_t s, uint64_t value, void *stream) {
+	NRC_REQUIRE(s, "nrc_external_semaphore_wait: null semaphore");
+	cudaExternalSemaphoreWaitParams p{};
+	p.params.fence.value = value;
+	if (cudaError_t e = cudaWaitExternalSemaphoresAsync(&s->sem, &p, 1, (cudaStream_t)stream); e != cudaSuccess)
+		return cuda_fail("cudaWaitExternalSemaphoresAsync", e);
+	return NRC_OK;
+}
+
+// ... and waits for `value` before the screen pass reads the composited image / the next frame reuses the records
+int nrc_external_semaphore_signal(nrc_external_semaphore_handle_t s, uint64_t value, void *stream) {
+	NRC_REQUIRE(s, "nrc_external_semaphore_signal: null semaphore");
+	cudaExternalSemaphoreSignalParams p{};
+	p.params.fence.value = value;
+	if (cudaError_t e = cudaSignalExternalSemaphoresAsync(&s->sem, &p, 1, (cudaStream_t)stream); e != cudaSuccess)
+		return cuda_fail("cudaSignalExternalSemaphoresAsync", e);
+	return NRC_OK;
+}
+
+int nrc_external_semaphore_release(nrc_external_semaphore_handle_t s) {
+	if (!s)
+		return NRC_OK;
+	cudaSetDevice(s->device);
+	const cudaError_t e = cudaDestroyExternalSemaphore(s->sem);
+	delete s;
+	return e == cudaSuccess ? NRC_OK : cuda_fail("cudaDestroyExternalSemaphore", e);
+}
+
 } // extern "C"

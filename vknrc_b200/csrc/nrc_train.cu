@@ -24,6 +24,7 @@
 // reference's 2.6 M fp32 atomics per batch, NN_nv.glsl:309-314,357-364), each CTA owning a slice of the 20 736 floats,
 // and (optionally) nrc_optimize.comp is applied verbatim to that slice -> grid barrier -> next batch of the frame.
 #include "nrc_kernels.h"
+#include <atomic>
 #include "nrc_encode.cuh"
 #include "nrc_unpack.cuh"
 #include <type_traits>
@@ -864,12 +865,16 @@ uint32_t gradient_max_partials(int sms) { return (uint32_t)sms; }
 template <int IN_MODE>
 static cudaError_t launch_train_t(const TrainParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, uint32_t grid, cudaStream_t stream) {
 	auto kern = nrc_train_kernel<IN_MODE>;
-	static bool configured = false;
-	if (!configured) {
+	static std::atomic<uint64_t> configured{0}; // function attributes are per device: one bit per device ordinal
+	int dev = 0;
+	if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess)
+		return e;
+	const uint64_t dev_bit = 1ull << (dev & 63);
+	if (!(configured.load(std::memory_order_acquire) & dev_bit)) {
 		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, train_smem_bytes(8));
 		if (e != cudaSuccess)
 			return e;
-		configured = true;
+		configured.fetch_or(dev_bit, std::memory_order_release);
 	}
 	cudaLaunchConfig_t cfg{};
 	cfg.gridDim = dim3(grid), cfg.blockDim = dim3(kTrainThreads), cfg.dynamicSmemBytes = train_smem_bytes(p.pool_tiles), cfg.stream = stream;
