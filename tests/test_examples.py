@@ -1,0 +1,41 @@
+"""The C++ drivers under examples/ (shaped like the reference's own callers, test/main.cpp and
+test/mlp_learning_an_image/main.cpp) run against the in-tree library through the C ABI only."""
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+EX = os.path.join(ROOT, "examples")
+
+
+def _binary(name):
+    path = os.path.join(EX, name)
+    if not os.path.exists(path):
+        pytest.skip(f"examples/{name} not built (python __graft_entry__.py builds it)")
+    return path
+
+
+def test_examples_only_use_the_public_header():
+    for src in ("mlp_harness.cpp", "learn_image.cpp"):
+        text = open(os.path.join(EX, src)).read()
+        includes = re.findall(r'#include\s+[<"]([^>"]+)[>"]', text)
+        assert "nrc_b200.h" in includes
+        assert not [i for i in includes if "csrc" in i or "oracle" in i or i.endswith(".cuh") or i.endswith(".hpp")], includes
+
+
+@pytest.mark.gpu
+def test_mlp_harness_matches_its_cpu_loop():
+    r = subprocess.run([_binary("mlp_harness")], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "U(-0.02, 0.02) weights: OK" in r.stdout and "He-normal weights: OK" in r.stdout, r.stdout
+
+
+@pytest.mark.gpu
+def test_learn_image_converges(tmp_path):
+    r = subprocess.run([_binary("learn_image"), "512"], capture_output=True, text=True, timeout=120, cwd=tmp_path)
+    assert r.returncode == 0, r.stdout + r.stderr
+    psnr = [float(m) for m in re.findall(r"PSNR ([0-9.]+) dB", r.stdout)]
+    assert len(psnr) >= 8 and psnr[-1] > psnr[0] + 5.0, r.stdout  # SGD lr 0.01 as the reference: slow but monotone
+    assert (tmp_path / "learn_image_out.ppm").stat().st_size > 640 * 640 * 3
