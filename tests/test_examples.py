@@ -18,11 +18,11 @@ def _binary(name):
 
 
 def test_examples_only_use_the_public_header():
-    for src in ("mlp_harness.cpp", "learn_image.cpp"):
+    for src in ("mlp_harness.cpp", "learn_image.cpp", "render_loop.cpp"):
         text = open(os.path.join(EX, src)).read()
         includes = re.findall(r'#include\s+[<"]([^>"]+)[>"]', text)
-        assert "nrc_b200.h" in includes
-        assert not [i for i in includes if "csrc" in i or "oracle" in i or i.endswith(".cuh") or i.endswith(".hpp")], includes
+        assert "nrc_b200.h" in includes or "nrc_b200.hpp" in includes
+        assert not [i for i in includes if "csrc" in i or "oracle" in i or i.endswith(".cuh") or (i.endswith(".hpp") and i != "nrc_b200.hpp")], includes
 
 
 @pytest.mark.gpu
@@ -39,3 +39,19 @@ def test_learn_image_converges(tmp_path):
     psnr = [float(m) for m in re.findall(r"PSNR ([0-9.]+) dB", r.stdout)]
     assert len(psnr) >= 8 and psnr[-1] > psnr[0] + 5.0, r.stdout  # SGD lr 0.01 as the reference: slow but monotone
     assert (tmp_path / "learn_image_out.ppm").stat().st_size > 640 * 640 * 3
+
+
+def test_cpp_wrapper_header_compiles_standalone(tmp_path):
+    """include/nrc_b200.hpp (the VkNRCState-shaped C++ face) needs nothing but the C header: plain g++, no CUDA."""
+    tu = tmp_path / "tu.cpp"
+    tu.write_text('#include <nrc_b200.hpp>\nint main() { return sizeof(nrc::State) == sizeof(void *) && sizeof(nrc::FrameBuffers) > 0 ? 0 : 1; }\n')
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    r = subprocess.run(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"), str(tu)],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.gpu
+def test_render_loop_learns_and_composites():
+    r = subprocess.run([_binary("render_loop"), "48"], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and r.stdout.strip().endswith("OK"), r.stdout + r.stderr
