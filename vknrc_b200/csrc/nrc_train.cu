@@ -19,7 +19,7 @@
 //   dW       l=5..0 : dW_l[64 x 64] += delta_l^T * a_l  (K = 128 samples, M=64) accumulated IN TMEM across all of the
 //                     CTA's tiles (5*64 + 16 fp32 columns), written once per CTA as a partial.
 //   Hand-offs are mbarriers only: a_ready (8 warp arrivals: operand stored + accumulator drained -> issuer),
-//   d_full (tcgen05.commit -> epilogue warps), tile_done (all MMAs of a tile complete).
+//   d_full (tcgen05.commit -> epilogue warps), tile_done (all MMAs of the CTA's last tile of a batch complete).
 // Then, in the same launch: grid barrier -> the partials are summed in a fixed order (deterministic, unlike the
 // reference's 2.6 M fp32 atomics per batch, NN_nv.glsl:309-314,357-364), each CTA owning a slice of the 20 736 floats,
 // and (optionally) nrc_optimize.comp is applied verbatim to that slice -> grid barrier -> next batch of the frame.
@@ -307,7 +307,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	uint32_t df_ph = 0, db_ph = 0;            // epilogue threads
 	uint32_t af_ph = 0, ab_ph = 0, d5_ph = 0; // issuer
 	uint32_t in_ph = 0, dw1_ph = 0;           // issuer: TMA input tiles, dw1_done
-	uint32_t tile_base = 0;                   // tiles of earlier batches of this launch (tile_done completes once per tile)
+	uint32_t done_ph = 0;                     // epilogue threads: tile_done completes once per batch in which the CTA had tiles
 
 	// The first tile of a batch is encoded ahead of time: for batch 0 right here (while the weights stream in), for batch
 	// b + 1 at the end of batch b's gradient phase - before the grid barriers, the reduction and the weight reload, none of
@@ -453,9 +453,11 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 #pragma unroll
 								for (int kk = 0; kk < 8; ++kk)
 									mma_ss_lh(tmem + 64 * l, dl + kk * 128, al + kk * 128, dhi, id_dw64, acc | (kk > 0));
-								if (l == 0)
+								if (l == 0 && !has_f) // the CTA's last tile of this batch: every dW accumulator is final
 									tc_commit(tile_done);
-								if (IN_MODE == NRC_IN_ENCODED && l == 1)
+								// (only where the wait below follows: every completed phase of dw1_done is consumed, so the
+								// waiter's parity can never drift from the barrier's - also across the batches of a launch)
+								if (IN_MODE == NRC_IN_ENCODED && l == 1 && has_f && r + 1 < my_tiles)
 									tc_commit(dw1_done);
 							}
 						}
@@ -654,7 +656,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			// staged in the last tile's a_1 / a_0 buffers (dead once every MMA has completed, and distinct from the buffers
 			// the earlier drains may still be copied out of by slower warps)
 			NRC_GTRACE(5);
-			mbar_wait(tile_done, (tile_base + my_tiles - 1) & 1);
+			mbar_wait(tile_done, done_ph);
+			done_ph ^= 1;
 			tc_fence_after();
 			NRC_GTRACE(6);
 			float *stage1 = (float *)(pool_sm + fin1 * 16384), *stage0 = (float *)(pool_sm + fin0 * 16384);
@@ -688,7 +691,6 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			encode_tile_row(tp.batch[b + 1], n_next, blockIdx.x, pool_sm);
 			arrive_ready(af_ready);
 		}
-		tile_base += my_tiles;
 		w_reloads += (b > 0 && my_tiles) ? 1u : 0u;
 
 		// ============================================================ deterministic reduction (+ optimizer step)
