@@ -80,3 +80,18 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "import oracle" not in text and "from oracle" not in text and "libnrc_oracle" not in text, f
+
+
+def test_headers_are_plain_c(tmp_path):
+    """The boundary is a C ABI: both public headers must compile as C99 with nothing but <stdint.h>."""
+    import subprocess
+    tu = tmp_path / "tu.c"
+    tu.write_text('#include <nrc_b200.h>\nint main(void) { nrc_config_t c = {1u, 1u, 0u}; NrcEvalRecord e; (void)c; (void)e;\n'
+                  '  return sizeof(NrcEvalRecord) == 20 && sizeof(NrcTrainRecord) == 40 && sizeof(NrcMaterial) == 64 &&\n'
+                  '         sizeof(NrcOptimizerEntry) == 16 && sizeof(NrcOptimizerState) == 20 && sizeof(NrcPrimRow) == 64 ? 0 : 1; }\n')
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    exe = tmp_path / "tu"
+    r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(tu), "-o", str(exe)],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    assert subprocess.run([str(exe)]).returncode == 0  # the struct sizes are the reference's (NRCRecord.glsl, Scene.glsl std430)
