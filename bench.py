@@ -139,8 +139,10 @@ def run_reference(args, rank: int, world: int):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    sample = 65536
-    steps, warm = max(1, min(args.steps, 8)), max(1, min(args.warmup, 2))
+    # exactly K timed steps after W warm-up steps, as for the GPU arm; each step is a bounded sample of the frame's queries,
+    # sized so that the whole run stays within about two minutes (~0.3 s per 65 536 queries on 16 host cores)
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    sample = 65536 if steps + warm <= 320 else max(4096, (65536 * 320 // (steps + warm)) // 128 * 128)
     os.environ["OMP_NUM_THREADS"] = str(threads)
     import oracle
     rng = np.random.default_rng(0)
