@@ -1,9 +1,11 @@
 // trace_grad.cu -- development tool: runs nrc_gradient_kernel built with -DNRC_TRACE on one 16384-record batch and
 // prints CTA 0 / thread 0's event timeline (tags: 1 entry, 2 setup done, 3 inputs ready, 0x1l fwd accumulator l ready,
 // 0x2l fwd epilogue l stored, 0x3l dA accumulator ready, 0x4l delta stored, 5 tile loop done, 6 dW complete, 7 dW
-// staged, 8 partial written, 9 grid barrier passed, 10 exit).
+// staged, 8 partial written, 9 grid barrier passed, 0x50-0x54 reduction (0x51 partials loaded, 0x58/0x52 tree, 0x55 gradient stored,
+// 0x56 Adam done, 0x57 CTA barrier), 10 exit).
 #include "../vknrc_b200/csrc/nrc_train.cu"
 #include <cstdio>
+#include <vector>
 typedef CUresult (*PFN)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                         const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static void mk(CUtensorMap *tm, void *base, uint64_t rows, uint32_t box) {
@@ -18,11 +20,27 @@ int main(int argc, char **argv) {
 	__half *w; float *rec, *tgt, *partials;
 	cudaMalloc(&w, 6 * 8192); cudaMalloc(&rec, n * 56); cudaMalloc(&tgt, n * 12); cudaMalloc(&partials, 148 * NRC_GRAD_STRIDE * 4);
 	cudaMemset(w, 0, 6 * 8192); cudaMemset(rec, 0x11, n * 56); cudaMemset(tgt, 0, n * 12);
+	{ // realistic values (He-normal-like weights, records and targets in [0, 1), optimizer moments of a run in progress): all-zero
+	  // buffers send every IEEE division of the Adam step through its slow path and distort the timeline
+		std::vector<__half> hw(6 * 4096); std::vector<float> hr(n * 14), ht(n * 3);
+		uint32_t x = 12345u; auto rnd = [&]() { x = x * 1664525u + 1013904223u; return (float)(x >> 8) * (1.0f / 16777216.0f); };
+		for (auto &v : hw) v = __float2half(0.6f * rnd() - 0.3f);
+		for (auto &v : hr) v = rnd();
+		for (auto &v : ht) v = rnd();
+		cudaMemcpy(w, hw.data(), hw.size() * 2, cudaMemcpyHostToDevice); cudaMemcpy(rec, hr.data(), hr.size() * 4, cudaMemcpyHostToDevice);
+		cudaMemcpy(tgt, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice);
+	}
 	CUtensorMap tw; mk(&tw, w, 323, 64);
 	const int nb = argc > 2 ? atoi(argv[2]) : 1; // batches per launch (frame = 4)
 	NrcOptimizerEntry *entries; NrcOptimizerState *ost; uint32_t *sync; float *grads; __half *uw;
 	cudaMalloc(&entries, 20672 * 16); cudaMalloc(&ost, 20); cudaMalloc(&sync, 32); cudaMalloc(&grads, NRC_GRAD_STRIDE * 4); cudaMalloc(&uw, 6 * 8192);
-	cudaMemset(entries, 0, 20672 * 16); cudaMemset(sync, 0, 32);
+	cudaMemset(sync, 0, 32);
+	{
+		std::vector<NrcOptimizerEntry> he(20672); std::vector<__half> hw(20672);
+		cudaMemcpy(hw.data(), w, 20672 * 2, cudaMemcpyDeviceToHost);
+		for (int i = 0; i < 20672; ++i) he[i] = NrcOptimizerEntry{1e-3f * (float)((i % 7) - 3), 1e-6f * (float)(1 + i % 5), __half2float(hw[i]), __half2float(hw[i])};
+		cudaMemcpy(entries, he.data(), he.size() * 16, cudaMemcpyHostToDevice);
+	}
 	const NrcOptimizerState st0{0u, 1.0f, 1.0f, 1.0f, 0.0f}; cudaMemcpy(ost, &st0, 20, cudaMemcpyHostToDevice);
 	nrc::TrainParams tp{};
 	for (int b = 0; b < nb; ++b) {

@@ -95,7 +95,9 @@ __device__ __forceinline__ NrcOptimizerState advance_state(const NrcOptimizerSta
 }
 __device__ __forceinline__ void adam_update(const AdamParams &a, uint32_t i, NrcOptimizerEntry e, float grad_sum, float count,
                                             const NrcOptimizerState &st) {
-	float g = __fdiv_rn(__fdiv_rn(grad_sum, count), NRC_LOSS_SCALE);
+	float g = __fdiv_rn(grad_sum, count);
+	if (NRC_LOSS_SCALE != 1.0f) // (x / 1 == x exactly: the second IEEE division of nrc_optimize.comp:36 is skipped, not approximated)
+		g = __fdiv_rn(g, NRC_LOSS_SCALE);
 	if (isnan(g) || isinf(g))
 		g = 0.0f;
 	e.m = __fadd_rn(__fmul_rn(NRC_ADAM_BETA1, e.m), __fmul_rn(1.0f - NRC_ADAM_BETA1, g));
@@ -775,6 +777,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 						count += scratch[w];
 					have_count = true;
 				}
+				NRC_GTRACE(0x58);
 				if (mine_blk) {
 					const float *col = &red_sm[threadIdx.x >> 6][0][(threadIdx.x & 63u) >> 2].x + (threadIdx.x & 3u);
 					float t[16];
@@ -823,10 +826,13 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 					const bool do_adam = adam_mode != 0 && total_count > 0.0f; // nrc_optimize.comp:33-34 / nrc_train_prepare.comp:22
 					any_adam = any_adam || do_adam;
 					tp.gradients[my_i] = tp.accumulate ? tp.gradients[my_i] + sum : sum;
+					NRC_GTRACE(0x55);
 					if (do_adam && my_i < NRC_WEIGHT_COUNT)
 						adam_update(adam, my_i, my_entry, sum, total_count, st);
+					NRC_GTRACE(0x56);
 				}
 				__syncthreads();
+				NRC_GTRACE(0x57);
 			}
 			NRC_GTRACE(0x53);
 			if (blockIdx.x == 0 && threadIdx.x == 0 && p.d_count) { // nrc_train_prepare.comp:17-19: write the clamped count back
