@@ -35,6 +35,7 @@ extern "C" {
 #define NRC_ERR_CUDA (-2)
 #define NRC_ERR_UNSUPPORTED_DEVICE (-3) /* not an sm_100 part: there is no fallback path */
 #define NRC_ERR_OUT_OF_MEMORY (-4)
+#define NRC_ERR_PEER_TIMEOUT (-5) /* multi-GPU: a peer's gradient words never arrived (nrc_comm_status) */
 
 #define NRC_B200_WEIGHT_COUNT 20672u
 #define NRC_B200_GRADIENT_FLOATS 20736u
@@ -135,6 +136,18 @@ int nrc_train_batch(nrc_handle_t h, const void *d_train_records, uint32_t *d_cou
 int nrc_train_frame(nrc_handle_t h, void *const d_train_records[4], uint32_t *const d_counts[4], uint32_t max_count,
                     const NrcScene *scene, void *stream);
 
+/* ---- one frame (src/rg/NRCRenderGraph.cpp) ----
+ * nrc_frame_begin == NRCRenderGraph::PreExecute's counter reset (:108-112): eval_count and batch_train_count[0..3] <- 0,
+ *   enqueued on `stream` BEFORE the caller's record producer (the path tracer) appends this frame's records.
+ * nrc_frame == the NN part of the graph in its order (:46-80): nn_inference_pass with last frame's use_weights (screen
+ *   composite + feedback into the train targets), then the four nn_train_pass groups on the counts the producer left,
+ *   use_weights republished by the last one (if its batch is not empty, nrc_optimize.comp:33-34). Two kernel launches,
+ *   no host synchronisation: the pair nrc_frame_begin / nrc_frame can be captured into a CUDA graph once and replayed. */
+int nrc_frame_begin(nrc_handle_t h, uint32_t *d_eval_count, uint32_t *const d_train_counts[4], void *stream);
+int nrc_frame(nrc_handle_t h, const void *d_eval_records, const uint32_t *d_eval_count, uint64_t max_eval_count,
+              const NrcScene *scene, void *d_bias_factor_r, const void *d_factor_gb, uint32_t image_pitch,
+              void *const d_train_records[4], uint32_t *const d_train_counts[4], void *stream);
+
 /* ---- training (NNTrain pass group: clear -> prepare -> gradient -> optimize, src/rg/NNTrain.hpp:95-127) ----
  * nrc_gradient_unpacked: gradient pass + deterministic batch reduction into the gradient buffer (replaces clear +
  *   nrc_gradient.comp's atomics). inputs as above; targets = 3 fp32 (`bias`, NRCRecord.glsl:36) `target_stride` apart.
@@ -160,17 +173,30 @@ int nrc_train_frame_unpacked(nrc_handle_t h, const void *const d_inputs[4], uint
 /* optional fp32 [max_count][3] buffer that receives the (unclamped) training predictions of the next gradient call */
 void nrc_set_prediction_capture(nrc_handle_t h, float *d_predictions);
 
-/* ---- multi-GPU (one process per GPU; records of every batch sharded per GPU) ----
- * The reference is single-GPU; this is the exchange step of the data-parallel path. nrc_comm_init allocates this rank's
- * inbox and returns its 64-byte CUDA IPC handle; the caller gathers the handles of all ranks (rank order) through its
- * own channel and passes them to nrc_comm_connect on every rank (then synchronises the ranks once). From then on every
- * nrc_gradient_* / nrc_train_* call all-reduces the reduced gradient (dW, loss sum, record count) with the peers INSIDE
- * the training kernel - peer-mapped stores over NVLink, per-block flags, fixed rank-order sum, so the result is
+/* ---- multi-GPU (records of every batch sharded per GPU) ----
+ * The reference is single-GPU; this is the exchange step of the data-parallel path. After set-up every nrc_gradient_* /
+ * nrc_train_* call all-reduces the reduced gradient (dW, loss sum, record count) with the peers INSIDE the training
+ * kernel - {epoch, value} words pushed into every peer's inbox over NVLink, fixed rank-order sum, so the result is
  * bit-identical on all ranks - and the optimizer step that follows is replicated. All ranks must make the same sequence
- * of training calls with the same max_count. */
+ * of training calls (max_count may differ per rank). Two ways to set up the inboxes:
+ *   (a) one process per GPU, CUDA IPC: nrc_comm_init allocates this rank's inbox and returns its 64-byte IPC handle; the
+ *       caller gathers the handles of all ranks (rank order) through its own channel and passes them to nrc_comm_connect
+ *       on every rank (then synchronises the ranks once). One unicast store per peer and word.
+ *   (b) caller-owned buffers, nrc_comm_attach: `d_inboxes[r]` = rank r's buffer of nrc_comm_buffer_bytes() as addressable
+ *       from this device - cudaDeviceEnablePeerAccess pointers in a single process that drives several GPUs, a
+ *       cuMemCreate / NCCL-window / torch-symmetric-memory allocation across processes. `d_multicast` (optional) is the
+ *       same set of buffers bound to one NVSwitch multicast object (cuMulticastCreate): the push is then ONE multimem.st
+ *       per word, replicated by the switch (NVLS). The local buffer is zeroed by the call; synchronise the ranks after it.
+ * A peer that does not show up within the timeout (nrc_comm_set_timeout, in polls of one word; default 2^24, about a
+ * second) does not hang or kill the GPU context: the waiting rank skips that batch's optimizer step and raises a flag
+ * that nrc_comm_status (synchronises `stream`) reports as NRC_ERR_PEER_TIMEOUT. */
 uint32_t nrc_comm_handle_bytes(void);
 int nrc_comm_init(nrc_handle_t h, uint32_t rank, uint32_t world, void *out_handle);
 int nrc_comm_connect(nrc_handle_t h, const void *all_handles);
+uint64_t nrc_comm_buffer_bytes(void);
+int nrc_comm_attach(nrc_handle_t h, uint32_t rank, uint32_t world, void *const *d_inboxes, void *d_multicast);
+int nrc_comm_status(nrc_handle_t h, void *stream);
+void nrc_comm_set_timeout(nrc_handle_t h, uint32_t polls);
 int nrc_comm_shutdown(nrc_handle_t h);
 uint32_t nrc_comm_world(nrc_handle_t h);
 

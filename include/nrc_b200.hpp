@@ -99,8 +99,12 @@ public:
 	// one frame in the order of src/rg/NRCRenderGraph.cpp:46-80: inference with last frame's use_weights (including the
 	// write-back into the train targets), then training - two kernel launches
 	void Frame(const FrameBuffers &f, const NrcScene &scene, void *stream) {
-		Infer(f, scene, stream);
-		TrainFrame(f, scene, stream);
+		Check(nrc_frame(m_handle, f.eval_records, f.eval_count, f.max_eval_count, &scene, f.bias_factor_r, f.factor_gb, f.image_pitch,
+		                const_cast<void *const *>(f.train_records), const_cast<uint32_t *const *>(f.train_counts), stream));
+	}
+	// NRCRenderGraph::PreExecute (:108-112): zero the frame's counters before the record producer runs
+	void FrameBegin(const FrameBuffers &f, void *stream) {
+		Check(nrc_frame_begin(m_handle, const_cast<uint32_t *>(f.eval_count), const_cast<uint32_t *const *>(f.train_counts), stream));
 	}
 
 	void Download(uint16_t *weights, uint16_t *use_weights, NrcOptimizerEntry *entries, NrcOptimizerState *state, float *gradients, void *stream) {

@@ -22,4 +22,7 @@ def test_fused_nvlink_allreduce_training(world):
     lines = [l for l in r.stdout.splitlines() if l.startswith("MGPU_RESULT ")]
     assert r.returncode == 0 and lines, r.stdout[-2000:] + r.stderr[-4000:]
     res = json.loads(lines[-1][len("MGPU_RESULT "):])
-    assert res["ok"] and res["replicated_bit_identical"] and res["count_ok"], res
+    assert res["ok"] and res["peer_timeout_reported"], res
+    for mode, m in res["modes"].items():
+        assert "unavailable" in m or (m["replicated_bit_identical"] and m["count_ok"]), (mode, m)
+    assert "unavailable" not in res["modes"]["ipc"], res

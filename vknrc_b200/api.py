@@ -143,6 +143,13 @@ SIGNATURES = {
     "nrc_comm_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "nrc_comm_shutdown": (C.c_int, [C.c_void_p]),
     "nrc_comm_world": (C.c_uint32, [C.c_void_p]),
+    "nrc_comm_buffer_bytes": (C.c_uint64, []),
+    "nrc_comm_attach": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(C.c_void_p), C.c_void_p]),
+    "nrc_comm_status": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "nrc_comm_set_timeout": (None, [C.c_void_p, C.c_uint32]),
+    "nrc_frame_begin": (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_void_p), C.c_void_p]),
+    "nrc_frame": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32,
+                            C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_void_p]),
     "nrc_set_prediction_capture": (None, [C.c_void_p, C.c_void_p]),
     "nrc_image_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.c_float, C.c_void_p]),
@@ -400,7 +407,44 @@ class NrcState:
         cns = (C.c_void_p * 4)(*[_ptr(t) for t in counts]) if counts is not None else None
         _check(lib().nrc_train_frame(self._h, recs, cns, n, C.byref(scene.c), _stream()))
 
+    # ---- one frame (src/rg/NRCRenderGraph.cpp:46-80, 100-113)
+    def frame_begin(self, eval_count, train_counts):
+        cns = (C.c_void_p * 4)(*[_ptr(t) for t in train_counts])
+        _check(lib().nrc_frame_begin(self._h, _ptr(eval_count), cns, _stream()))
+
+    def frame(self, eval_records, eval_count, scene: "DeviceScene", bias_factor_r, factor_gb, image_pitch, train_records, train_counts,
+              max_eval_count=None):
+        n = eval_records.numel() * eval_records.element_size() // 20 if max_eval_count is None else max_eval_count
+        recs = (C.c_void_p * 4)(*[_ptr(t) for t in train_records])
+        cns = (C.c_void_p * 4)(*[_ptr(t) for t in train_counts])
+        _check(lib().nrc_frame(self._h, _ptr(eval_records), _ptr(eval_count), n, C.byref(scene.c), _ptr(bias_factor_r), _ptr(factor_gb),
+                               image_pitch, recs, cns, _stream()))
+
     # ---- multi-GPU (one process per GPU)
+    def comm_attach_symmetric(self, group=None, multicast: bool = True):
+        """nrc_comm_attach on a torch symmetric-memory allocation (cuMem + NVSwitch multicast object, mapped into every rank by
+        torch.distributed._symmetric_memory - plumbing): with `multicast` the in-kernel exchange pushes every word with ONE
+        multimem.st through the switch instead of one store per peer. Returns True if a multicast mapping was attached."""
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        group = group if group is not None else dist.group.WORLD
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        nbytes = lib().nrc_comm_buffer_bytes()
+        self._symm = symm_mem.empty(nbytes // 8, dtype=torch.int64, device=f"cuda:{self.device}")
+        self._symm_handle = symm_mem.rendezvous(self._symm, group)
+        ptrs = (C.c_void_p * world)(*[int(p) for p in self._symm_handle.buffer_ptrs])
+        mc = int(self._symm_handle.multicast_ptr) if multicast else 0
+        _check(lib().nrc_comm_attach(self._h, rank, world, ptrs, mc or None))
+        dist.barrier(group)  # nobody pushes before everybody has zeroed and attached
+        return bool(mc)
+
+    def comm_status(self):
+        _check(lib().nrc_comm_status(self._h, _stream()))
+
+    def comm_set_timeout(self, polls: int):
+        lib().nrc_comm_set_timeout(self._h, polls)
+
     def comm_connect(self, group=None):
         """Sets up the in-kernel NVLink all-reduce between the ranks of a torch.distributed group: every rank allocates
         its inbox, the 64-byte IPC handles are all-gathered (plumbing), every rank maps its peers' inboxes."""

@@ -12,7 +12,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libnrc_b200.so")
 SOURCES = ["nrc_infer.cu", "nrc_train.cu", "nrc_state.cu"]
-HEADERS = ["sm100_ptx.cuh", "nrc_config.h", "nrc_kernels.h", "nrc_encode.cuh", "nrc_unpack.cuh", "nrc_state.hpp", "../../include/nrc_b200.h"]
+HEADERS = ["sm100_ptx.cuh", "nrc_config.h", "nrc_kernels.h", "nrc_encode.cuh", "nrc_unpack.cuh", "nrc_state.hpp", "../../include/nrc_b200.h",
+           "../../include/nrc_b200_types.h"]
+STAMP = os.path.join(HERE, "build", "build_stamp.json")  # what the last build ran: written by build(), read by tests / the driver
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "-Xptxas", "-v"]
 
@@ -24,8 +26,22 @@ def _nvcc() -> str:
     raise RuntimeError("nvcc not found")
 
 
+def source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted(SOURCES + HEADERS):
+        h.update(open(os.path.join(CSRC, f), "rb").read())
+    return h.hexdigest()
+
+
 def needs_build() -> bool:
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
+        return True
+    try:
+        import json
+        if json.load(open(STAMP)).get("source_sha256") != source_hash():
+            return True  # (content, not mtime: a checkout or a snapshot copy rewrites every mtime)
+    except Exception:
         return True
     t = os.path.getmtime(LIB)
     deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
@@ -60,6 +76,17 @@ def build(force: bool = False, verbose: bool = False, extra_flags=(), out: str =
         raise RuntimeError("link failed")
     with open(os.path.join(objdir, "ptxas.log"), "w") as f:
         f.write("\n".join(log))
+    if out == LIB:
+        import hashlib
+        import json
+        import time
+        ver = subprocess.run([_nvcc(), "--version"], stdout=subprocess.PIPE, text=True, env=env).stdout.strip().splitlines()[-1]
+        h = hashlib.sha256()
+        for f in sorted(SOURCES + HEADERS):
+            h.update(open(os.path.join(CSRC, f), "rb").read())
+        with open(STAMP, "w") as f:
+            json.dump({"built_at": time.time(), "nvcc": ver, "flags": NVCC_FLAGS, "sources": SOURCES, "source_sha256": h.hexdigest(),
+                       "kernels_ptxas_lines": sum(l.count("Used ") for l in log)}, f)
     if verbose:
         print("\n".join(log))
     return out

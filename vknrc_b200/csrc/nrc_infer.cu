@@ -96,7 +96,9 @@ __device__ __forceinline__ void write_result(const InferParams &p, uint64_t gi, 
 	} else if (p.out_mode == NRC_OUT_RGBA8) {
 		((uint32_t *)p.out)[gi] = pack_rgba8(y0, y1, y2);
 	} else { // NRC_OUT_SCATTER
-		y0 = fmaxf(y0, 0.0f), y1 = fmaxf(y1, 0.0f), y2 = fmaxf(y2, 0.0f);
+		// NNOutput3 hands the prediction over as fp16 widened to fp32 (NN_nv.glsl:148-158), then max(., 0) (nrc_inference.comp:48)
+		y0 = fmaxf(__half2float(__float2half_rn(y0)), 0.0f), y1 = fmaxf(__half2float(__float2half_rn(y1)), 0.0f),
+		y2 = fmaxf(__half2float(__float2half_rn(y2)), 0.0f);
 		const uint32_t dst = pf.dst;
 		if (dst == NRC_EVAL_INVALID_DST)
 			return;

@@ -93,22 +93,28 @@ struct AdamParams {
 	int use_ema;
 };
 
-// Multi-GPU exchange (one process per GPU, records of every batch sharded per GPU): after the local reduction each
-// rank pushes its reduced 64-float blocks straight into every peer's inbox over NVLink (peer-mapped device memory)
-// as 8-byte {value, epoch} words - one NVLink traversal, no fence, the receiver spins on the very word it needs -
-// and adds the R copies in rank order: an all-reduce fused into the training kernel, bit-identical on every rank,
-// followed by a replicated Adam step. A per-block word carries the rank's record count the same way.
+// Multi-GPU exchange (one process per GPU, or one process driving several GPUs; records of every batch sharded per
+// GPU): after the local reduction each rank pushes its reduced 64-float blocks into every peer's inbox over NVLink as
+// 8-byte {epoch, value} words - ONE multimem.st through the NVSwitch multicast mapping of the inboxes (NVLS) when the
+// caller attached one, else one st.relaxed.sys per peer into peer-mapped memory. One traversal carries data and flag,
+// no fence, the receiver spins on the very word it needs and adds the R copies in rank order: an all-reduce fused into
+// the training kernel, bit-identical on every rank, followed by a replicated Adam step. Each rank's record count
+// travels the same way in ONE word per source (written by the rank's CTA 0, polled by every CTA of the receiver), so
+// nothing in the layout depends on a rank's grid size.
 // Comm buffer of a rank (identical layout everywhere, zero-initialised; parity = epoch & 1 double-buffers it):
 //   uint64_t data [2 parities][NRC_MAX_RANKS sources][NRC_GRAD_STRIDE]        (epoch << 32 | float bits)
-//   uint64_t count[2 parities][NRC_MAX_RANKS sources][NRC_GRAD_STRIDE / 64]   (epoch << 32 | count float bits)
+//   uint64_t count[2 parities][NRC_MAX_RANKS sources]                         (epoch << 32 | count float bits)
 #define NRC_MAX_RANKS 8
 struct CommParams {
 	uint32_t rank, world;           // world <= 1: no exchange
 	uint32_t *epoch_word;           // device word: epochs used so far; batch b of a launch uses epoch *epoch_word + 1 + b (never 0)
 	uint64_t *inbox[NRC_MAX_RANKS]; // comm buffer of every rank as mapped into this process (inbox[rank] = the local one)
+	uint64_t *multicast;            // the same buffers through one multicast mapping (stores land in every rank's inbox), or nullptr
+	uint32_t *error_word;           // device word, set to 1 when a peer's word did not arrive within spin_limit polls
+	uint32_t spin_limit;            // polls of one word before giving up (the launch then finishes without an optimizer step)
 };
 constexpr size_t kCommDataWords = 2ull * NRC_MAX_RANKS * NRC_GRAD_STRIDE;
-constexpr size_t kCommCountWords = 2ull * NRC_MAX_RANKS * (NRC_GRAD_STRIDE / 64);
+constexpr size_t kCommCountWords = 2ull * NRC_MAX_RANKS;
 constexpr size_t kCommBytes = (kCommDataWords + kCommCountWords) * sizeof(uint64_t);
 
 // One launch of nrc_train_kernel = up to NRC_TRAIN_BATCH_COUNT dependent training batches (a frame):
@@ -143,5 +149,6 @@ cudaError_t launch_prim_table(const NrcScene &scene, uint32_t prim_count, void *
 cudaError_t launch_adam(const AdamParams &p, cudaStream_t stream);
 cudaError_t launch_sgd(const SgdParams &p, cudaStream_t stream);
 uint32_t gradient_max_partials(int sms);
+constexpr uint32_t kMaxTrainGrid = 160; // the in-kernel reduction sums at most 16 groups x 10 partials
 
 } // namespace nrc

@@ -69,6 +69,31 @@ int make_weight_tensor_map(CUtensorMap *tm, const void *d_weights, std::string *
 int make_input_tensor_map(CUtensorMap *tm, const void *d_inputs, uint64_t rows, std::string *err) {
 	return make_map(tm, d_inputs, rows, NRC_TILE, err);
 }
+// A tensor map depends only on (base, rows, box): a renderer passes the same few buffers every frame, so the encoded
+// descriptors are kept (cuTensorMapEncodeTiled costs ~1 us of host time per call, up to 9 per host-buffer inference).
+int NrcState::cached_map(CUtensorMap *tm, const void *base, uint64_t rows, uint32_t box_rows, std::string *err) {
+	for (MapEntry &e : m_maps)
+		if (e.base == base && e.rows == rows && e.box == box_rows) {
+			e.stamp = ++m_map_clock;
+			*tm = e.map;
+			return NRC_OK;
+		}
+	int rc = make_map(tm, base, rows, box_rows, err);
+	if (rc != NRC_OK)
+		return rc;
+	MapEntry *slot = nullptr;
+	if (m_maps.size() < kMapCacheEntries) {
+		m_maps.emplace_back();
+		slot = &m_maps.back();
+	} else {
+		slot = &m_maps[0];
+		for (MapEntry &e : m_maps)
+			if (e.stamp < slot->stamp)
+				slot = &e;
+	}
+	slot->base = base, slot->rows = rows, slot->box = box_rows, slot->stamp = ++m_map_clock, slot->map = *tm;
+	return NRC_OK;
+}
 
 static int check_device(int device, int *sms, std::string *err) {
 	cudaDeviceProp prop;
@@ -77,12 +102,12 @@ static int check_device(int device, int *sms, std::string *err) {
 		*err = std::string("cudaGetDeviceProperties: ") + cudaGetErrorString(e);
 		return NRC_ERR_CUDA;
 	}
-	if (prop.major != 10) { // the kernels are sm_100a-only (tcgen05 / TMEM); there is deliberately no other path
+	if (prop.major != 10 || prop.minor != 0) { // the library holds one sm_100a cubin (tcgen05 / TMEM): no other device can load it
 		*err = std::string("device '") + prop.name + "' is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
 		       "; this library only runs on sm_100 (B200)";
 		return NRC_ERR_UNSUPPORTED_DEVICE;
 	}
-	*sms = prop.multiProcessorCount;
+	*sms = prop.multiProcessorCount < (int)kMaxTrainGrid ? prop.multiProcessorCount : (int)kMaxTrainGrid;
 	return NRC_OK;
 }
 
@@ -148,13 +173,13 @@ int NrcState::CommInit(uint32_t rank, uint32_t world, cudaIpcMemHandle_t *out_ha
 	NRC_CUDA_TRY(cudaMemset(m_comm_local, 0, kCommBytes), sink);
 	NRC_CUDA_TRY(cudaDeviceSynchronize(), sink);
 	NRC_CUDA_TRY(cudaIpcGetMemHandle(out_handle, m_comm_local), sink);
-	m_comm_rank = rank, m_comm_world = world;
-	NRC_CUDA_TRY(cudaMemset(m_sync_words + 4, 0, sizeof(uint32_t)), sink); // exchange epochs restart with the fresh (zeroed) inboxes
+	m_comm_rank = rank, m_comm_world = world, m_comm_owned = true;
+	NRC_CUDA_TRY(cudaMemset(m_sync_words + 4, 0, 2 * sizeof(uint32_t)), sink); // exchange epochs restart with the fresh (zeroed) inboxes; error word cleared
 	return NRC_OK;
 }
 int NrcState::CommConnect(const cudaIpcMemHandle_t *all_handles) {
 	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
-	if (!m_comm_local || !all_handles)
+	if (!m_comm_local || !m_comm_owned || !all_handles)
 		return fail(NRC_ERR_INVALID_ARGUMENT, "CommConnect: call CommInit first");
 	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
 	for (uint32_t r = 0; r < m_comm_world; ++r) {
@@ -169,15 +194,53 @@ int NrcState::CommConnect(const cudaIpcMemHandle_t *all_handles) {
 	m_comm_connected = true;
 	return NRC_OK;
 }
+// Caller-owned exchange buffers: any allocation every rank can address works - cudaDeviceEnablePeerAccess mappings in a
+// single process that drives several GPUs, cuMemCreate / cuMulticastCreate, an NCCL window, torch symmetric memory.
+// `multicast` (optional) maps all the inboxes through one NVSwitch multicast object: the push becomes one multimem.st.
+int NrcState::CommAttach(uint32_t rank, uint32_t world, void *const *inboxes, void *multicast) {
+	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
+	if (world < 1 || world > NRC_MAX_RANKS || rank >= world || !inboxes)
+		return fail(NRC_ERR_INVALID_ARGUMENT, "CommAttach: need rank < world <= 8 and world inbox pointers");
+	for (uint32_t r = 0; r < world; ++r)
+		if (!inboxes[r] || ((uintptr_t)inboxes[r] & 7u))
+			return fail(NRC_ERR_INVALID_ARGUMENT, "CommAttach: every inbox must be a mapped, 8-byte aligned device pointer");
+	if ((uintptr_t)multicast & 7u)
+		return fail(NRC_ERR_INVALID_ARGUMENT, "CommAttach: the multicast pointer must be 8-byte aligned");
+	CommShutdown();
+	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
+	for (uint32_t r = 0; r < world; ++r)
+		m_comm_inbox[r] = (uint64_t *)inboxes[r];
+	m_comm_local = m_comm_inbox[rank], m_comm_multicast = (uint64_t *)multicast;
+	m_comm_rank = rank, m_comm_world = world, m_comm_owned = false;
+	NRC_CUDA_TRY(cudaMemset(m_comm_local, 0, kCommBytes), sink); // (the caller synchronises the ranks after attaching, before the first training call)
+	NRC_CUDA_TRY(cudaMemset(m_sync_words + 4, 0, 2 * sizeof(uint32_t)), sink);
+	NRC_CUDA_TRY(cudaDeviceSynchronize(), sink);
+	m_comm_connected = true;
+	return NRC_OK;
+}
 int NrcState::CommShutdown() {
-	for (uint32_t r = 0; r < NRC_MAX_RANKS; ++r) {
-		if (m_comm_inbox[r] && m_comm_inbox[r] != m_comm_local)
-			cudaIpcCloseMemHandle(m_comm_inbox[r]);
-		m_comm_inbox[r] = nullptr;
+	if (m_comm_owned) {
+		for (uint32_t r = 0; r < NRC_MAX_RANKS; ++r)
+			if (m_comm_inbox[r] && m_comm_inbox[r] != m_comm_local)
+				cudaIpcCloseMemHandle(m_comm_inbox[r]);
+		if (m_comm_local)
+			cudaFree(m_comm_local);
 	}
-	if (m_comm_local)
-		cudaFree(m_comm_local);
-	m_comm_local = nullptr, m_comm_connected = false, m_comm_world = 1, m_comm_rank = 0;
+	for (uint32_t r = 0; r < NRC_MAX_RANKS; ++r)
+		m_comm_inbox[r] = nullptr;
+	m_comm_local = m_comm_multicast = nullptr, m_comm_connected = false, m_comm_owned = false, m_comm_world = 1, m_comm_rank = 0;
+	return NRC_OK;
+}
+// Synchronises `stream` and reports whether any exchange since the last set-up gave up waiting for a peer.
+int NrcState::CommStatus(cudaStream_t stream) {
+	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
+	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
+	NRC_CUDA_TRY(cudaStreamSynchronize(stream), sink);
+	uint32_t flag = 0;
+	NRC_CUDA_TRY(cudaMemcpy(&flag, m_sync_words + 5, sizeof(flag), cudaMemcpyDeviceToHost), sink);
+	if (flag)
+		return fail(NRC_ERR_PEER_TIMEOUT, "a peer's gradient words did not arrive within the exchange timeout; the optimizer step of that batch was skipped "
+		                                  "and the replicas may have diverged (re-synchronise the weights, then nrc_comm_init / nrc_comm_attach again)");
 	return NRC_OK;
 }
 
@@ -205,11 +268,15 @@ int NrcState::upload_initial(const float *w) {
 	}
 	const NrcOptimizerState st{0u, 1.0f, 1.0f, 1.0f, 0.0f}; // src/VkNRCState.cpp:50
 	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
+	// (blocking copies on the legacy stream do not order against the library's non-blocking streams: drain the device first,
+	// so that no training launch in flight sees half-written weights)
+	NRC_CUDA_TRY(cudaDeviceSynchronize(), sink);
 	NRC_CUDA_TRY(cudaMemcpy(m_weights, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice), sink);
 	NRC_CUDA_TRY(cudaMemcpy(m_use_weights, h.data(), h.size() * sizeof(__half), cudaMemcpyHostToDevice), sink);
 	NRC_CUDA_TRY(cudaMemcpy(m_optimizer_entries, e.data(), e.size() * sizeof(NrcOptimizerEntry), cudaMemcpyHostToDevice), sink);
 	NRC_CUDA_TRY(cudaMemcpy(m_optimizer_state, &st, sizeof(st), cudaMemcpyHostToDevice), sink);
-	NRC_CUDA_TRY(cudaMemset(m_sync_words, 0, 4 * sizeof(uint32_t)), sink); // (not [4]: exchange epochs only restart with fresh inboxes)
+	NRC_CUDA_TRY(cudaMemset(m_sync_words, 0, sizeof(uint32_t)), sink); // only the optimizer's "last CTA" counter: the grid-barrier counter
+	                                                                 // is monotonic and base-relative, the exchange epochs restart only with fresh inboxes
 	return NRC_OK;
 }
 
@@ -236,9 +303,9 @@ int NrcState::Infer(InferParams p, const void *encoded_inputs, const __half *wei
 		return NRC_OK;
 	CUtensorMap tm_w, tm_in;
 	std::string err;
-	int rc = make_weight_tensor_map(&tm_w, weights, &err);
+	int rc = cached_map(&tm_w, weights, NRC_WEIGHT_ROWS, 64, &err);
 	if (rc == NRC_OK)
-		rc = p.in_mode == NRC_IN_ENCODED ? make_input_tensor_map(&tm_in, encoded_inputs, p.n, &err) : (tm_in = tm_w, NRC_OK);
+		rc = p.in_mode == NRC_IN_ENCODED ? cached_map(&tm_in, encoded_inputs, p.n, NRC_TILE, &err) : (tm_in = tm_w, NRC_OK);
 	if (rc != NRC_OK)
 		return fail(rc, err);
 	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
@@ -264,13 +331,14 @@ int NrcState::InferEncodedHost(const void *h_inputs, void *h_outputs, uint64_t n
 	if (n > m_stage_capacity) { // (re-allocation synchronises the device: a one-time cost per size)
 		cudaFree(m_stage_in), cudaFree(m_stage_out);
 		m_stage_in = m_stage_out = nullptr, m_stage_capacity = 0;
+		m_maps.clear(); // (descriptors of the freed staging buffer must not outlive it)
 		NRC_CUDA_TRY(cudaMalloc(&m_stage_in, n * 128), sink);
 		NRC_CUDA_TRY(cudaMalloc(&m_stage_out, n * 6), sink);
 		m_stage_capacity = n;
 	}
 	CUtensorMap tm_w, tm_in;
 	std::string err;
-	int rc = make_weight_tensor_map(&tm_w, weights, &err);
+	int rc = cached_map(&tm_w, weights, NRC_WEIGHT_ROWS, 64, &err);
 	if (rc != NRC_OK)
 		return fail(rc, err);
 	// equal chunks of whole 128-query tiles (the host -> device copies are the long pole: everything else hides under them)
@@ -288,7 +356,7 @@ int NrcState::InferEncodedHost(const void *h_inputs, void *h_outputs, uint64_t n
 		NRC_CUDA_TRY(cudaStreamWaitEvent(stream, m_ev_in[c], 0), sink);
 		InferParams p{};
 		p.n = cnt, p.in_mode = NRC_IN_ENCODED, p.out_mode = NRC_OUT_F16VEC3, p.clamp_output = clamp_output, p.out = (uint8_t *)m_stage_out + first * 6;
-		rc = make_input_tensor_map(&tm_in, (const uint8_t *)m_stage_in + first * 128, cnt, &err);
+		rc = cached_map(&tm_in, (const uint8_t *)m_stage_in + first * 128, cnt, NRC_TILE, &err);
 		if (rc != NRC_OK)
 			return fail(rc, err);
 		NRC_CUDA_TRY(launch_infer(p, tm_w, tm_in, m_sms, stream), sink);
@@ -311,9 +379,9 @@ int NrcState::Train(TrainParams tp, const void *encoded_inputs, const __half *we
 		return fail(NRC_ERR_INVALID_ARGUMENT, "Train: pre-encoded inputs are single-batch");
 	CUtensorMap tm_w, tm_in;
 	std::string err;
-	int rc = make_weight_tensor_map(&tm_w, weights, &err);
+	int rc = cached_map(&tm_w, weights, NRC_WEIGHT_ROWS, 64, &err);
 	if (rc == NRC_OK)
-		rc = encoded ? make_input_tensor_map(&tm_in, encoded_inputs, tp.batch[0].n, &err) : (tm_in = tm_w, NRC_OK);
+		rc = encoded ? cached_map(&tm_in, encoded_inputs, tp.batch[0].n, NRC_TILE, &err) : (tm_in = tm_w, NRC_OK);
 	if (rc != NRC_OK)
 		return fail(rc, err);
 	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
@@ -326,6 +394,7 @@ int NrcState::Train(TrainParams tp, const void *encoded_inputs, const __half *we
 	tp.comm = CommParams{};
 	if (m_comm_connected && m_comm_world > 1 && !tp.accumulate) { // (the handle-less test-harness calls never exchange)
 		tp.comm.rank = m_comm_rank, tp.comm.world = m_comm_world, tp.comm.epoch_word = m_sync_words + 4;
+		tp.comm.error_word = m_sync_words + 5, tp.comm.spin_limit = m_comm_spin_limit, tp.comm.multicast = m_comm_multicast;
 		for (uint32_t r = 0; r < m_comm_world; ++r)
 			tp.comm.inbox[r] = m_comm_inbox[r];
 	}
@@ -470,6 +539,19 @@ int nrc_comm_shutdown(nrc_handle_t h) {
 	return h->state.CommShutdown();
 }
 uint32_t nrc_comm_world(nrc_handle_t h) { return h ? h->state.comm_world() : 0u; }
+uint64_t nrc_comm_buffer_bytes(void) { return (uint64_t)kCommBytes; }
+int nrc_comm_attach(nrc_handle_t h, uint32_t rank, uint32_t world, void *const *d_inboxes, void *d_multicast) {
+	NRC_REQUIRE(h && d_inboxes, "nrc_comm_attach: null argument");
+	return h->state.CommAttach(rank, world, d_inboxes, d_multicast);
+}
+int nrc_comm_status(nrc_handle_t h, void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	return h->state.CommStatus((cudaStream_t)stream);
+}
+void nrc_comm_set_timeout(nrc_handle_t h, uint32_t polls) {
+	if (h)
+		h->state.CommSetTimeout(polls);
+}
 
 int nrc_mlp_evaluate_encoded(const void *d_weights, const void *d_inputs, void *d_outputs, uint64_t n, void *stream) {
 	if (n == 0)
@@ -670,6 +752,31 @@ int nrc_train_frame(nrc_handle_t h, void *const d_records[4], uint32_t *const d_
 	}
 	tp.num_batches = NRC_TRAIN_BATCH_COUNT, tp.gradients = h->state.GetGradientBuffer(), tp.limit = NRC_GRAD_STRIDE, tp.batch_cap = max_count;
 	return h->state.Train(tp, nullptr, h->state.GetWeightBuffer(), (cudaStream_t)stream);
+}
+
+// ---- one frame of the render graph, NN part (src/rg/NRCRenderGraph.cpp): PreExecute's counter reset (:108-112), then - after
+// the caller's record producer - the nn_inference_pass (:46-55) and the four nn_train_pass groups (:57-80)
+int nrc_frame_begin(nrc_handle_t h, uint32_t *d_eval_count, uint32_t *const d_train_counts[4], void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	NRC_REQUIRE(d_eval_count && d_train_counts, "nrc_frame_begin: null count pointer");
+	if (cudaError_t e = cudaMemsetAsync(d_eval_count, 0, sizeof(uint32_t), (cudaStream_t)stream); e != cudaSuccess)
+		return set_error(NRC_ERR_CUDA, std::string("nrc_frame_begin: ") + cudaGetErrorString(e));
+	for (int b = 0; b < NRC_TRAIN_BATCH_COUNT; ++b) {
+		NRC_REQUIRE(d_train_counts[b], "nrc_frame_begin: null batch count pointer");
+		if (cudaError_t e = cudaMemsetAsync(d_train_counts[b], 0, sizeof(uint32_t), (cudaStream_t)stream); e != cudaSuccess)
+			return set_error(NRC_ERR_CUDA, std::string("nrc_frame_begin: ") + cudaGetErrorString(e));
+	}
+	return NRC_OK;
+}
+int nrc_frame(nrc_handle_t h, const void *d_eval_records, const uint32_t *d_eval_count, uint64_t max_eval_count, const NrcScene *scene,
+              void *d_bias_factor_r, const void *d_factor_gb, uint32_t image_pitch, void *const d_train_records[4],
+              uint32_t *const d_train_counts[4], void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	NRC_REQUIRE(d_train_records && d_train_counts, "nrc_frame: null buffer table");
+	int rc = nrc_infer(h, d_eval_records, d_eval_count, max_eval_count, scene, d_bias_factor_r, d_factor_gb, image_pitch, d_train_records, stream);
+	if (rc != NRC_OK)
+		return rc;
+	return nrc_train_frame(h, d_train_records, d_train_counts, NRC_TRAIN_BATCH_SIZE, scene, stream);
 }
 
 static int check_unpacked_args(const char *who, const void *d_inputs, uint32_t input_stride, const void *d_targets, uint32_t target_stride,

@@ -6,6 +6,7 @@
 #pragma once
 #include <random>
 #include <string>
+#include <vector>
 
 #include "nrc_kernels.h"
 
@@ -78,7 +79,10 @@ public:
 	// the peers inside the kernel (peer-mapped inboxes over NVLink) before the replicated optimizer step.
 	int CommInit(uint32_t rank, uint32_t world, cudaIpcMemHandle_t *out_handle); // allocates the local inbox
 	int CommConnect(const cudaIpcMemHandle_t *all_handles);                      // world handles in rank order
+	int CommAttach(uint32_t rank, uint32_t world, void *const *inboxes, void *multicast); // caller-owned buffers (+ optional NVLS mapping)
 	int CommShutdown();
+	int CommStatus(cudaStream_t stream);             // NRC_ERR_PEER_TIMEOUT after an exchange gave up on a peer
+	void CommSetTimeout(uint32_t polls) { m_comm_spin_limit = polls ? polls : 1u; }
 	uint32_t comm_world() const { return m_comm_connected ? m_comm_world : 1; }
 	int AdamStep(bool write_use_weights, cudaStream_t stream);
 	int SgdStep(float lr, float batch, cudaStream_t stream);
@@ -91,6 +95,16 @@ public:
 private:
 	int fail(int code, const std::string &what);
 	int upload_initial(const float *fp32_weights);
+	int cached_map(CUtensorMap *tm, const void *base, uint64_t rows, uint32_t box_rows, std::string *err);
+	struct MapEntry {
+		const void *base;
+		uint64_t rows, stamp;
+		uint32_t box;
+		CUtensorMap map;
+	};
+	static constexpr size_t kMapCacheEntries = 32;
+	std::vector<MapEntry> m_maps;
+	uint64_t m_map_clock{0};
 
 	int m_device{0}, m_sms{0};
 	Extent2D m_extent{};
@@ -103,8 +117,8 @@ private:
 	NrcOptimizerEntry *m_optimizer_entries{nullptr};
 	float *m_gradients{nullptr}, *m_partials{nullptr};
 	uint32_t *m_sync_words{nullptr}; // [0] optimizer "last CTA" counter, [2] grid-barrier arrival counter (monotonic), [3] its
-	                                 // base for the next launch, [4] multi-GPU exchange epochs used so far - all device-resident,
-	                                 // so a captured CUDA graph of the training calls replays correctly
+	                                 // base for the next launch, [4] multi-GPU exchange epochs used so far, [5] exchange error
+	                                 // flag - all device-resident, so a captured CUDA graph of the training calls replays correctly
 	float *m_prediction_capture{nullptr};
 
 	// host-buffer path: device staging (grown on demand), copy-in / copy-out streams, per-chunk events
@@ -114,10 +128,11 @@ private:
 	cudaStream_t m_stream_in{nullptr}, m_stream_out{nullptr};
 	cudaEvent_t m_ev_start{nullptr}, m_ev_in[kHostChunks]{}, m_ev_done[kHostChunks]{}, m_ev_out{nullptr};
 
-	uint64_t *m_comm_local{nullptr};
+	uint64_t *m_comm_local{nullptr}, *m_comm_multicast{nullptr};
 	uint64_t *m_comm_inbox[NRC_MAX_RANKS]{};
 	uint32_t m_comm_rank{0}, m_comm_world{1};
-	bool m_comm_connected{false};
+	uint32_t m_comm_spin_limit{1u << 24}; // ~ a second of polling per word before a peer is declared missing
+	bool m_comm_connected{false}, m_comm_owned{false};
 
 	uint32_t m_seed{0};
 	std::mt19937 m_rng;

@@ -168,17 +168,27 @@ __device__ __forceinline__ float ld_cg(const float *p) { // L2 only: the partial
 
 // 8-byte {epoch, payload} words exchanged with peer GPUs: a single store is atomic, so the receiver can spin on the word
 __device__ __forceinline__ void st_peer(uint64_t *p, uint64_t v) { asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
-__device__ __forceinline__ uint32_t wait_peer(const uint64_t *p, uint32_t epoch) {
-	uint64_t got;
-	for (uint32_t spins = 0;; ++spins) {
-		asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(p) : "memory");
-		if ((uint32_t)(got >> 32) == epoch)
-			return (uint32_t)got;
-		if (spins > (1u << 24)) // a peer never showed up (~seconds): fail loudly instead of hanging the GPU
-			__trap();
-		if (spins > 16)
-			__nanosleep(32);
+// the same word through the NVSwitch multicast mapping: one store, replicated by the switch into every rank's inbox
+__device__ __forceinline__ void st_multicast(uint64_t *p, uint64_t v) { asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory"); }
+// Bounded wait for a peer's word. A peer that never shows up (crashed, or entered the launch `spin_limit` polls late) must
+// neither hang the GPU nor kill the context: the waiter raises the handle's error word (reported by nrc_comm_status as
+// NRC_ERR_PEER_TIMEOUT), stops waiting for the rest of the launch, and its CTA skips the optimizer step of this batch.
+__device__ __forceinline__ uint32_t wait_peer(const uint64_t *p, uint32_t epoch, const CommParams &comm, bool &timed_out) {
+	uint64_t got = 0;
+	if (!timed_out) {
+		for (uint32_t spins = 0;; ++spins) {
+			asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(p) : "memory");
+			if ((uint32_t)(got >> 32) == epoch)
+				return (uint32_t)got;
+			if (spins > comm.spin_limit)
+				break;
+			if (spins > 16)
+				__nanosleep(32);
+		}
+		timed_out = true;
+		atomicExch(comm.error_word, 1u);
 	}
+	return 0u;
 }
 __device__ __forceinline__ float4 ld_cg4(const float *p) {
 	float4 v;
@@ -339,20 +349,22 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		if (b > 0 && my_tiles && warp < kEpiWarps) {
 			// Re-stage the weights the previous batch's optimizer phase just wrote (by other SMs; the grid barrier made them
 			// visible in L2): plain 16-byte L2 loads into the swizzled tile, no global cross-proxy fence needed. Rows past 323
-			// keep the zeros TMA filled in for batch 0.
+			// are written as zeros (what TMA's out-of-bounds fill does in batch 0).
 			const uint4 *src = (const uint4 *)tp.adam.weights;
-			constexpr int kPerThread = (NRC_WEIGHT_ROWS * 8 + kEpiThreads - 1) / kEpiThreads; // 11: every load in flight at once
+			constexpr int kChunks = NRC_LAYERS * 64 * 8;                         // 16-byte chunks of the 384-row tile
+			constexpr int kPerThread = (kChunks + kEpiThreads - 1) / kEpiThreads; // 12: every load in flight at once
 			uint4 v[kPerThread];
 #pragma unroll
 			for (int u = 0; u < kPerThread; ++u) {
 				const uint32_t idx = threadIdx.x + u * kEpiThreads;
+				v[u] = make_uint4(0u, 0u, 0u, 0u); // rows 323..383 pad W_5 with zeros: a CTA that had no tile in batch 0 never ran the TMA load
 				if (idx < NRC_WEIGHT_ROWS * 8)
 					asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + idx));
 			}
 #pragma unroll
 			for (int u = 0; u < kPerThread; ++u) {
 				const uint32_t idx = threadIdx.x + u * kEpiThreads, r = idx >> 3, c = idx & 7u;
-				if (idx < NRC_WEIGHT_ROWS * 8)
+				if (idx < (uint32_t)kChunks)
 					*(uint4 *)(w_sm + r * 128 + ((c ^ (r & 7u)) << 4)) = v[u];
 			}
 			fence_proxy_async_smem();
@@ -731,7 +743,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			// partials g, g + 16, g + 32, ... (all loads in flight at once), and the 16 group sums are combined by a
 			// fixed binary tree. Every order is fixed => bit-reproducible.
 			const uint32_t lane16 = threadIdx.x & 15u, grp = (threadIdx.x >> 4) & 15u;
-			bool any_adam = false;
+			bool any_adam = false, have_peer_counts = false;
 			for (uint32_t blk0 = blockIdx.x; blk0 < kReduceBlocks; blk0 += 3 * gridDim.x) {
 				// the optimizer entry of "my" element of this round is independent of the sums: fetch it first
 				const uint32_t my_blk = blk0 + (threadIdx.x >> 6) * gridDim.x, my_i = my_blk * 64 + (threadIdx.x & 63u);
@@ -793,37 +805,50 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 					sum = t[0];
 				}
 				float total_count = count;
+				bool cta_timed_out = false;
 				if (world > 1) {
-					// ---- all-reduce over NVLink, fused: push {value, epoch} words into every peer's inbox, spin on the
-					// peers' words in my own inbox, add in rank order (identical operands in identical order on every rank)
-					const size_t dslot = (size_t)parity * NRC_MAX_RANKS * NRC_GRAD_STRIDE, cslot = kCommDataWords + (size_t)parity * NRC_MAX_RANKS * kReduceBlocks;
+					// ---- all-reduce over NVLink, fused: push {value, epoch} words into every peer's inbox (one multicast store
+					// through the switch, or one store per peer), spin on the peers' words in my own inbox, add in rank order
+					// (identical operands in identical order on every rank)
+					const size_t dslot = (size_t)parity * NRC_MAX_RANKS * NRC_GRAD_STRIDE, cslot = kCommDataWords + (size_t)parity * NRC_MAX_RANKS;
 					const uint64_t tag = (uint64_t)epoch << 32;
-					if (mine_blk)
-						for (uint32_t r = 0; r < world; ++r)
-							if (r != me)
-								st_peer(tp.comm.inbox[r] + dslot + (size_t)me * NRC_GRAD_STRIDE + my_i, tag | __float_as_uint(sum));
-					if (threadIdx.x >= 192 && threadIdx.x < 192 + NRC_MAX_RANKS) { // one thread per peer: the record counts
-						const uint32_t r = threadIdx.x - 192;
-						uint32_t peer_count = 0;
-						if (r < world && r != me) {
-							st_peer(tp.comm.inbox[r] + cslot + (size_t)me * kReduceBlocks + blk0, tag | __float_as_uint(count));
-							peer_count = wait_peer(tp.comm.inbox[me] + cslot + (size_t)r * kReduceBlocks + blk0, epoch);
+					bool timed_out = false;
+					if (mine_blk) {
+						const size_t at = dslot + (size_t)me * NRC_GRAD_STRIDE + my_i;
+						if (tp.comm.multicast) {
+							st_multicast(tp.comm.multicast + at, tag | __float_as_uint(sum));
+						} else {
+							for (uint32_t r = 0; r < world; ++r)
+								if (r != me)
+									st_peer(tp.comm.inbox[r] + at, tag | __float_as_uint(sum));
 						}
-						peer_counts[r] = peer_count;
+					}
+					if (!have_peer_counts && threadIdx.x >= 192 && threadIdx.x < 192 + NRC_MAX_RANKS) { // one thread per peer: the record counts
+						const uint32_t r = threadIdx.x - 192;
+						if (blockIdx.x == 0) { // this rank's count: one word per source, published once per batch by CTA 0
+							if (tp.comm.multicast) {
+								if (r == me)
+									st_multicast(tp.comm.multicast + cslot + me, tag | __float_as_uint(count));
+							} else if (r < world && r != me) {
+								st_peer(tp.comm.inbox[r] + cslot + me, tag | __float_as_uint(count));
+							}
+						}
+						peer_counts[r] = r < world && r != me ? wait_peer(tp.comm.inbox[me] + cslot + r, epoch, tp.comm, timed_out) : 0u;
 					}
 					if (mine_blk) {
 						float tot = 0.0f;
 						for (uint32_t r = 0; r < world; ++r)
-							tot += r == me ? sum : __uint_as_float(wait_peer(tp.comm.inbox[me] + dslot + (size_t)r * NRC_GRAD_STRIDE + my_i, epoch));
+							tot += r == me ? sum : __uint_as_float(wait_peer(tp.comm.inbox[me] + dslot + (size_t)r * NRC_GRAD_STRIDE + my_i, epoch, tp.comm, timed_out));
 						sum = tot;
 					}
-					__syncthreads();
+					cta_timed_out = __syncthreads_or(timed_out ? 1 : 0) != 0;
+					have_peer_counts = true;
 					total_count = 0.0f;
 					for (uint32_t r = 0; r < world; ++r)
 						total_count += r == me ? count : __uint_as_float(peer_counts[r]); // integers < 2^24: exact
 				}
 				if (mine) {
-					const bool do_adam = adam_mode != 0 && total_count > 0.0f; // nrc_optimize.comp:33-34 / nrc_train_prepare.comp:22
+					const bool do_adam = adam_mode != 0 && total_count > 0.0f && !cta_timed_out; // nrc_optimize.comp:33-34 / nrc_train_prepare.comp:22
 					any_adam = any_adam || do_adam;
 					tp.gradients[my_i] = tp.accumulate ? tp.gradients[my_i] + sum : sum;
 					NRC_GTRACE(0x55);
