@@ -287,3 +287,188 @@ def unpack(scene: Scene, packed: np.ndarray) -> np.ndarray:
     out = np.empty((pk.shape[0], 14), np.float32)
     lib().nrc_oracle_unpack_batch(C.addressof(scene._c), pk.ctypes.data, pk.shape[0], 16, out)
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# The reference's own GLSL shaders compiled as C++ (oracle/glsl, built into _ref_glsl/libvknrc_glsl.so by the Makefile
+# where /root/reference exists; the prebuilt file travels to the GPU box). This is what pins encode / unpack / dst codec /
+# loss gradients / backward / dW / optimizer: reference SOURCE executed, not a restatement of it.
+# ---------------------------------------------------------------------------------------------------------------------
+_glsl = None
+
+
+class _GlslTexture(C.Structure):
+    _fields_ = [("texels", C.c_void_p), ("width", C.c_uint32), ("height", C.c_uint32)]
+
+
+class _GlslScene(C.Structure):
+    _fields_ = [("vertices", C.c_void_p), ("vertex_indices", C.c_void_p), ("texcoords", C.c_void_p), ("texcoord_indices", C.c_void_p),
+                ("materials", C.c_void_p), ("material_ids", C.c_void_p), ("transforms", C.c_void_p), ("textures", C.c_void_p),
+                ("texture_count", C.c_uint32), ("material_count", C.c_uint32)]
+
+
+def glsl_available() -> bool:
+    return os.path.exists(os.path.join(_HERE, "_ref_glsl", "libvknrc_glsl.so"))
+
+
+def glsl() -> C.CDLL:
+    global _glsl
+    if _glsl is None:
+        path = os.path.join(_HERE, "_ref_glsl", "libvknrc_glsl.so")
+        if not os.path.exists(path):
+            build()
+        G = C.CDLL(path)
+        vp, u32, u64 = C.c_void_p, C.c_uint32, C.c_uint64
+        G.glsl_NRCInputEncode.argtypes = [_f32p, u64, _u16p]
+        G.glsl_UnpackNRCInput.argtypes = [vp, _u32p, u64, _f32p]
+        G.glsl_EncodeNRCEvalDstScreen.argtypes = [u32, u32]
+        G.glsl_EncodeNRCEvalDstScreen.restype = u32
+        G.glsl_EncodeNRCEvalDstTrain.argtypes = [u32, u32, u32]
+        G.glsl_EncodeNRCEvalDstTrain.restype = u32
+        G.glsl_DecodeNRCEvalDst.argtypes = [u32] + [C.POINTER(u32)] * 4
+        G.glsl_evaluate_NV.argtypes = [_u16p, _u16p, u64, _u16p, C.c_int]
+        G.glsl_train_NV.argtypes = [_u16p, _f32p, _u16p, _u16p, u64, C.c_int]
+        G.glsl_nrc_inference.argtypes = [vp, vp, u32, _u16p, _f32p, _f32p, u32, u32, C.POINTER(vp), C.c_int]
+        G.glsl_nrc_gradient.argtypes = [vp, vp, u32, _u16p, _f32p, C.c_int]
+        G.glsl_nrc_train_prepare.argtypes = [C.POINTER(u32), C.POINTER(u32 * 3), C.POINTER(OptimizerState)]
+        G.glsl_nrc_optimize.argtypes = [_u16p, vp, _f32p, vp, u32, C.POINTER(OptimizerState), u32]
+        G.glsl_image_gradient.argtypes = [_u16p, _f32p, vp, u32, u32, u32, u32, u32, C.c_int]
+        G.glsl_image_optimize.argtypes = [_u16p, _f32p, _f32p]
+        G.glsl_image_inference.argtypes = [_u16p, vp, C.c_int]
+        G.glsl_image_uv.argtypes = [u32, u32, u32, C.POINTER(C.c_float), C.POINTER(C.c_float)]
+        G.glsl_image_oneblob32.argtypes = [C.c_float, C.c_float, _u16p]
+        _glsl = G
+    return _glsl
+
+
+def _glsl_scene(scene: "Scene"):
+    tex = (_GlslTexture * max(1, len(scene.textures)))()
+    for i, t in enumerate(scene.textures):
+        tex[i] = _GlslTexture(t.ctypes.data, t.shape[1], t.shape[0])
+    s = _GlslScene(scene.vertices.ctypes.data, scene.vertex_indices.ctypes.data, scene.texcoords.ctypes.data, scene.texcoord_indices.ctypes.data,
+                   scene.materials.ctypes.data, scene.material_ids.ctypes.data, scene.transforms.ctypes.data, C.addressof(tex),
+                   len(scene.textures), scene.materials.shape[0])
+    return s, tex  # (keep `tex` alive while `s` is in use)
+
+
+def glsl_encode(unpacked14) -> np.ndarray:
+    """NRCInputEncode of shader/src/NRCRecord.glsl:78-95, the reference's source: [n,14] fp32 -> [n,64] fp16."""
+    x = np.ascontiguousarray(unpacked14, np.float32).reshape(-1, 14)
+    out = np.empty((x.shape[0], 64), np.uint16)
+    glsl().glsl_NRCInputEncode(x, x.shape[0], out)
+    return out.view(np.float16)
+
+
+def glsl_unpack(scene: "Scene", packed) -> np.ndarray:
+    """UnpackNRCInput of shader/src/NRCRecord.glsl:98-125 over Scene.glsl, the reference's source."""
+    pk = np.ascontiguousarray(packed, np.uint32).reshape(-1, 4)
+    out = np.empty((pk.shape[0], 14), np.float32)
+    s, keep = _glsl_scene(scene)
+    glsl().glsl_UnpackNRCInput(C.addressof(s), pk, pk.shape[0], out)
+    return out
+
+
+def glsl_dst_screen(x, y):
+    return glsl().glsl_EncodeNRCEvalDstScreen(x, y)
+
+
+def glsl_dst_train(b, l, r):
+    return glsl().glsl_EncodeNRCEvalDstTrain(b, l, r)
+
+
+def glsl_dst_decode(e):
+    t, a, b, c = (C.c_uint32() for _ in range(4))
+    glsl().glsl_DecodeNRCEvalDst(e, C.byref(t), C.byref(a), C.byref(b), C.byref(c))
+    return t.value, a.value, b.value, c.value
+
+
+def glsl_evaluate_nv(weights, inputs, parallel=True) -> np.ndarray:
+    """test/evaluate_NV.comp dispatched over n/128 workgroups: [n,3] fp16."""
+    w, x = _bits(weights).reshape(-1), _bits(inputs).reshape(-1, 64)
+    out = np.empty((x.shape[0], 3), np.uint16)
+    assert glsl().glsl_evaluate_NV(w, x, x.shape[0], out, int(parallel)) == 0
+    return out.view(np.float16)
+
+
+def glsl_train_nv(weights, inputs, targets16, dw=None, parallel=False) -> np.ndarray:
+    """test/train_NV.comp (L2 loss): dW [20672] fp32, accumulated into `dw` by fp32 atomics as the shader does."""
+    w, x, t = _bits(weights).reshape(-1), _bits(inputs).reshape(-1, 64), _bits(targets16).reshape(-1)
+    dw = np.zeros(WEIGHT_COUNT, np.float32) if dw is None else dw
+    assert glsl().glsl_train_NV(w, dw, x, t, x.shape[0], int(parallel)) == 0
+    return dw
+
+
+def glsl_nrc_inference(scene, eval_records, eval_count, weights, bias_factor_r, factor_gb, train_records, parallel=True):
+    """shader/src/nrc_inference.comp in place on bias_factor_r [H,W,4] f32 / train_records (4 byte arrays of 40 B records)."""
+    s, keep = _glsl_scene(scene)
+    h, w_ = bias_factor_r.shape[0], bias_factor_r.shape[1]
+    ptrs = (C.c_void_p * 4)(*[r.ctypes.data for r in train_records])
+    ev = np.ascontiguousarray(eval_records)
+    assert glsl().glsl_nrc_inference(C.addressof(s), ev.ctypes.data, eval_count, _bits(weights).reshape(-1), bias_factor_r.reshape(-1),
+                                     np.ascontiguousarray(factor_gb, np.float32).reshape(-1), w_, h, ptrs, int(parallel)) == 0
+
+
+def glsl_nrc_gradient(scene, train_records, count, weights, dw=None, parallel=False) -> np.ndarray:
+    """shader/src/nrc_gradient.comp: dW accumulated by fp32 atomics (un-normalised)."""
+    s, keep = _glsl_scene(scene)
+    dw = np.zeros(WEIGHT_COUNT, np.float32) if dw is None else dw
+    tr = np.ascontiguousarray(train_records)
+    assert glsl().glsl_nrc_gradient(C.addressof(s), tr.ctypes.data, count, _bits(weights).reshape(-1), dw, int(parallel)) == 0
+    return dw
+
+
+class GlslOptimizer:
+    """nrc_train_prepare.comp + nrc_optimize.comp of the reference driven like src/rg/NNTrain.cpp: same interface as Optimizer."""
+
+    def __init__(self, fp32_weights):
+        w = np.asarray(fp32_weights, np.float32).reshape(WEIGHT_COUNT)
+        self.state = OptimizerState.initial()
+        self.entries = np.zeros(WEIGHT_COUNT, OPT_ENTRY_DTYPE)
+        self.entries["weight"] = w
+        self.entries["ema_weight"] = w
+        self.weights = w.astype(np.float16).view(np.uint16).copy()
+        self.use_weights = self.weights.copy()
+
+    def step(self, gradients, count, write_use_weights, use_ema) -> int:
+        c, cmd = C.c_uint32(count), (C.c_uint32 * 3)()
+        glsl().glsl_nrc_train_prepare(C.byref(c), C.byref(cmd), C.byref(self.state))
+        self.last_command = tuple(cmd)
+        g = np.ascontiguousarray(gradients, np.float32)
+        glsl().glsl_nrc_optimize(self.weights, self.use_weights.ctypes.data if write_use_weights else None, g, self.entries.ctypes.data,
+                                 c.value, C.byref(self.state), int(use_ema))
+        return c.value
+
+
+def glsl_image_uv(seed_x, seed_y, n) -> np.ndarray:
+    out = np.empty((n, 2), np.float32)
+    u, v = C.c_float(), C.c_float()
+    for g in range(n):
+        glsl().glsl_image_uv(seed_x & 0xFFFFFFFF, seed_y & 0xFFFFFFFF, g, C.byref(u), C.byref(v))
+        out[g] = (u.value, v.value)
+    return out
+
+
+def glsl_image_oneblob32(uv) -> np.ndarray:
+    uv = np.asarray(uv, np.float32).reshape(-1, 2)
+    out = np.empty((uv.shape[0], 64), np.uint16)
+    for i in range(uv.shape[0]):
+        glsl().glsl_image_oneblob32(float(uv[i, 0]), float(uv[i, 1]), out[i])
+    return out.view(np.float16)
+
+
+def glsl_image_gradient(weights, image_rgba8, seed_x, seed_y, n=16384, dw=None, parallel=False) -> np.ndarray:
+    img = np.ascontiguousarray(image_rgba8, np.uint8)
+    dw = np.zeros(WEIGHT_COUNT, np.float32) if dw is None else dw
+    assert glsl().glsl_image_gradient(_bits(weights).reshape(-1), dw, img.ctypes.data, img.shape[1], img.shape[0], seed_x & 0xFFFFFFFF,
+                                      seed_y & 0xFFFFFFFF, n, int(parallel)) == 0
+    return dw
+
+
+def glsl_image_optimize(weights16, fp_weights, gradients):
+    glsl().glsl_image_optimize(_bits(weights16), fp_weights, np.ascontiguousarray(gradients, np.float32))
+
+
+def glsl_image_inference(weights, parallel=True) -> np.ndarray:
+    out = np.empty((640, 640, 4), np.uint8)
+    assert glsl().glsl_image_inference(_bits(weights).reshape(-1), out.ctypes.data, int(parallel)) == 0
+    return out

@@ -836,9 +836,33 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 						peer_counts[r] = r < world && r != me ? wait_peer(tp.comm.inbox[me] + cslot + r, epoch, tp.comm, timed_out) : 0u;
 					}
 					if (mine_blk) {
+						// all peers' words are requested at once and polled together (one L2 round trip when they have arrived, instead
+						// of one per peer: 7 dependent round trips were 2.5 us of every 8-GPU exchange), then added in rank order
+						const uint64_t *src = tp.comm.inbox[me] + dslot + my_i;
+						uint32_t val[NRC_MAX_RANKS];
+						uint32_t pending = ((1u << world) - 1u) & ~(1u << me);
+						for (uint32_t spins = 0; pending && !timed_out; ++spins) {
+							uint64_t got[NRC_MAX_RANKS];
+#pragma unroll
+							for (uint32_t r = 0; r < NRC_MAX_RANKS; ++r)
+								if (pending >> r & 1u)
+									asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got[r]) : "l"(src + (size_t)r * NRC_GRAD_STRIDE) : "memory");
+#pragma unroll
+							for (uint32_t r = 0; r < NRC_MAX_RANKS; ++r)
+								if ((pending >> r & 1u) && (uint32_t)(got[r] >> 32) == epoch)
+									val[r] = (uint32_t)got[r], pending &= ~(1u << r);
+							if (pending && spins > tp.comm.spin_limit) {
+								timed_out = true;
+								atomicExch(tp.comm.error_word, 1u);
+							}
+							if (pending && spins > 16)
+								__nanosleep(32);
+						}
 						float tot = 0.0f;
-						for (uint32_t r = 0; r < world; ++r)
-							tot += r == me ? sum : __uint_as_float(wait_peer(tp.comm.inbox[me] + dslot + (size_t)r * NRC_GRAD_STRIDE + my_i, epoch, tp.comm, timed_out));
+#pragma unroll
+						for (uint32_t r = 0; r < NRC_MAX_RANKS; ++r)
+							if (r < world)
+								tot += r == me ? sum : (pending >> r & 1u) ? 0.0f : __uint_as_float(val[r]);
 						sum = tot;
 					}
 					cta_timed_out = __syncthreads_or(timed_out ? 1 : 0) != 0;
