@@ -7,14 +7,19 @@ training records/s, with tensor-pipe roofline fraction), one JSON line on stdout
 Workload (config.workload): BASELINE.json configs[2] -- 1920x1080 = 2 073 600 synthetic pre-encoded path-vertex queries
 ([n][64] fp16, the layout of test/evaluate_NV.comp) through the 64-wide fp16 MLP, random He-normal weights; one "step"
 = one pass over that batch. `value` = queries/s with inputs resident in HBM (CUDA events around exactly K launches,
-max over ranks); `e2e` = the same call fed from pinned HOST buffers with the H2D / D2H copies inside the timed region.
-`extra` carries the other half of the metric (training records/s on configs[3], 4 x 16384 records per frame) and the
-fused-encode inference path. Multi-GPU: queries (and training records) are sharded by index range, one process per
-GPU, weak scaling; training all-reduces the 82 944-byte gradient buffer INSIDE the training kernel (peer-mapped inboxes
-over NVLink) before a replicated Adam step; the NCCL version of the same frame is timed beside it.
+max over ranks); `e2e` = the same frame through the reference-facing C-ABI call on HOST buffers - the queries as the
+reference stores them (20-byte NRCEvalRecords) in pinned host memory in, fp16x3 radiance per query in host memory out,
+copies inside the timed region. `train` carries the other half of the metric (training records/s on configs[3],
+4 x 16384 records per frame, and the 2^20-records throughput step with its roofline), `multi_gpu` the data-parallel
+proofs (replicas bit-identical, fused exchange vs NCCL, configs[3] sharded as written), `extra` the remaining
+inference paths. Multi-GPU: queries (and training records) are sharded by index range, one process per GPU, weak
+scaling; training all-reduces the 82 944-byte gradient buffer INSIDE the training kernel (multimem.st through the
+NVSwitch multicast mapping where the box has NVLS) before a replicated Adam step; a run whose replicas are not
+bit-identical exits non-zero.
 
---impl reference times the reference's OWN CPU implementation of the same path (test/main.cpp `Evaluate`, compiled
-unmodified into oracle/_ref) on the host cores, on a bounded sample of the same workload.
+--impl reference times the reference's OWN CPU implementation of the same path (test/main.cpp `Evaluate` and `Train`,
+compiled unmodified into oracle/_ref) on the host cores, on the SAME configuration: the whole 2 073 600-query frame per
+step, the number of steps capped to a wall-clock budget.
 """
 from __future__ import annotations
 
@@ -95,35 +100,75 @@ class ClockSampler:
 
 
 def bind_to_gpu_numa_node(index: int):
-    """Best effort: run this rank (and therefore first-touch its pinned host buffers) on the CPUs of the NUMA node its GPU
-    hangs off, so that N ranks do not all stream their e2e inputs out of one socket's memory. Returns the node or None."""
+    """Best effort: run this rank (and therefore first-touch its pinned host buffers) on the CPUs next to its GPU, so that N
+    ranks do not all stream their e2e inputs out of one socket's memory. Sources, in order: the PCI device's numa_node in
+    sysfs, NVML's CPU affinity of the device (what `nvidia-smi topo -m` prints). Returns a description or None."""
+    cpus, how = set(), None
     try:
         import torch
         p = torch.cuda.get_device_properties(index)
         bdf = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
         node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
-        if node < 0:
-            return None
-        cpus = set()
-        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
-            lo, _, hi = part.partition("-")
-            cpus.update(range(int(lo), int(hi or lo) + 1))
+        if node >= 0:
+            for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+            how = f"sysfs numa_node {node}"
+    except Exception:
+        pass
+    if not cpus:
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            words = (os.cpu_count() + 63) // 64
+            mask = pynvml.nvmlDeviceGetCpuAffinity(h, words)
+            for w, bits in enumerate(mask):
+                for b in range(64):
+                    if bits >> b & 1:
+                        cpus.add(64 * w + b)
+            how = "nvml cpu affinity"
+        except Exception:
+            pass
+    try:
         cpus &= os.sched_getaffinity(0)
-        if cpus:
+        if cpus and cpus != os.sched_getaffinity(0):
             os.sched_setaffinity(0, cpus)
-            return node
+            return f"{how}: {len(cpus)} cpus"
+        if cpus:
+            return f"{how}: all {len(cpus)} cpus (single node)"
     except Exception:
         pass
     return None
 
 
-def cpu_reference_rate(sample: int, repeats: int, threads: int):
-    """queries/s of the reference's CPU `Evaluate` (oracle/_ref) on `sample` queries, best-of-median over repeats."""
-    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
-    import oracle
+class quiet_stdout:
+    """The reference's CPU `Train` prints its activations (test/main.cpp:43-72): keep fd 1 clean for the one JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        null = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(null, 1)
+        os.close(null)
+
+    def __exit__(self, *a):
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+def reference_inputs(n: int):
     rng = np.random.default_rng(0)
     w16 = (rng.standard_normal(20672) * np.sqrt(2 / 64)).astype(np.float32).astype(np.float16)
-    x = rng.uniform(0, 1, (sample, 64)).astype(np.float16)
+    x = rng.random((n, 64), dtype=np.float32).astype(np.float16)
+    return w16, x
+
+
+def cpu_reference_rate(sample: int, repeats: int, threads: int):
+    """queries/s of the reference's CPU `Evaluate` (oracle/_ref) on `sample` queries, median over repeats."""
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    import oracle
+    w16, x = reference_inputs(sample)
     kind = "reference" if oracle.ref_available() else "port"
     fn = (lambda: oracle.ref_evaluate(w16, x)) if kind == "reference" else (lambda: oracle.evaluate(w16, x, oracle.ACC_FP16_CHUNK16))
     fn()
@@ -135,34 +180,66 @@ def cpu_reference_rate(sample: int, repeats: int, threads: int):
     return sample / float(np.median(ts)), kind, ts
 
 
+def cpu_reference_train_rate(records: int, repeats: int, threads: int):
+    """records/s of the reference's CPU `Train` (test/main.cpp:29-74, oracle/_ref) on one batch of `records` records (the paper's
+    batch is 16384). SURVEY Q13: `Train` is the reference's own CPU cost of a training step, not a faithful backward pass."""
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    import oracle
+    w16, x = reference_inputs(records)
+    t16 = np.random.default_rng(1).random((records, 3), dtype=np.float32).astype(np.float16)
+    kind = "reference" if oracle.ref_available() else "port"
+    if kind == "reference":
+        fn = lambda: oracle.ref_train(w16, x, t16)
+    else:
+        fn = lambda: oracle.gradient(w16, x, t16.astype(np.float32), oracle.LOSS_L2, 1.0, oracle.ACC_FP16_CHUNK16)
+    ts = []
+    with quiet_stdout():
+        fn()
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+    return records / float(np.median(ts)), kind, ts
+
+
+REFERENCE_BUDGET_S = 150.0  # wall-clock budget of the timed region of the reference arm
+
+
 def run_reference(args, rank: int, world: int):
+    """The reference's own CPU implementation of the path (test/main.cpp `Evaluate`, compiled unmodified into oracle/_ref) on the
+    host cores, SAME CONFIG as the GPU arm: every step evaluates the whole 1920x1080 frame (2 073 600 pre-encoded queries). One
+    frame takes seconds on the host, so the NUMBER of steps is capped to a wall-clock budget (never the frame): `steps` is what
+    ran, `steps_requested` what was asked for."""
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    # exactly K timed steps after W warm-up steps, as for the GPU arm; each step is a bounded sample of the frame's queries,
-    # sized so that the whole run stays within about two minutes (~0.3 s per 65 536 queries on 16 host cores)
-    steps, warm = max(1, args.steps), max(0, args.warmup)
-    sample = 65536 if steps + warm <= 320 else max(4096, (65536 * 320 // (steps + warm)) // 128 * 128)
     os.environ["OMP_NUM_THREADS"] = str(threads)
     import oracle
-    rng = np.random.default_rng(0)
-    w16 = (rng.standard_normal(20672) * np.sqrt(2 / 64)).astype(np.float32).astype(np.float16)
-    x = rng.uniform(0, 1, (sample, 64)).astype(np.float16)
+    nq = int(os.environ.get("NRC_BENCH_REF_QUERIES", N_QUERIES))  # (tests shrink the frame; same_config is then false)
+    w16, x = reference_inputs(nq)
     kind = "reference" if oracle.ref_available() else "port"
     fn = (lambda: oracle.ref_evaluate(w16, x)) if kind == "reference" else (lambda: oracle.evaluate(w16, x, oracle.ACC_FP16_CHUNK16))
-    for _ in range(warm):
-        fn()
+    t0 = time.perf_counter()
+    fn()  # warm-up (one whole frame; further warm-up passes would only burn the budget)
+    t_step = time.perf_counter() - t0
+    steps = int(max(1, min(args.steps, REFERENCE_BUDGET_S // max(t_step, 1e-3))))
     t0 = time.perf_counter()
     for _ in range(steps):
         fn()
     dt = time.perf_counter() - t0
-    value = sample * steps / dt
-    desc = f"{sample} of {N_QUERIES} queries per step ({'test/main.cpp Evaluate, Eigen fp16, -O3 -mavx2 -mf16c -mfma -fopenmp' if kind == 'reference' else 'oracle port'})"
+    value = nq * steps / dt
+    train_rate, _, train_ts = cpu_reference_train_rate(16384, 2, threads)
+    desc = (f"{'all ' if nq == N_QUERIES else ''}{nq} queries of the {N_QUERIES}-query frame per step, {steps} steps "
+            f"({'test/main.cpp Evaluate, Eigen fp16, -O3 -mavx2 -mf16c -mfma -fopenmp' if kind == 'reference' else 'oracle port'})")
     print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
-        "ms_per_step": dt / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16",
-        "data": "synthetic", "config": {"workload": WORKLOAD, "queries_per_step_sampled": sample, "queries_per_frame": N_QUERIES},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": 1,
+        "steps_requested": args.steps, "warmup_requested": args.warmup, "ms_per_step": dt / steps * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "queries_per_gpu_per_step": nq, "queries_per_step": nq, "same_config": nq == N_QUERIES,
+                   "network": "64->5x(64,ReLU)->3, fp16 weights, fp16 accumulate (Eigen _Float16)", "host_threads": threads},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
+        "cpu_baseline_train": {"value": train_rate, "unit": "records/s", "cores": threads, "kind": kind,
+                               "sample": "one 16384-record batch, test/main.cpp Train (a debugging sketch of the backward pass, SURVEY Q13), median of 2"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
@@ -183,10 +260,12 @@ def main():
     import torch
     import torch.distributed as dist
     import vknrc_b200 as nrc
+    from vknrc_b200 import synth
+    from vknrc_b200.dist import shard_range
 
     assert torch.cuda.is_available(), "bench.py needs a GPU (there is no CPU fallback; use --impl reference for the CPU arm)"
     torch.cuda.set_device(local)
-    numa = bind_to_gpu_numa_node(local) if world > 1 else None  # pinned e2e buffers then live next to this rank's GPU
+    numa = bind_to_gpu_numa_node(local)  # pinned e2e buffers then live next to this rank's GPU
     dev = f"cuda:{local}"
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -217,42 +296,47 @@ def main():
         barrier()
         return max_over_ranks(e0.elapsed_time(e1)) / steps
 
+    peaks = measured_peaks()
     st = nrc.NrcState(local, (1920, 1080), seed=1234)  # replicated weights: same seed on every rank
     g = torch.Generator(device=dev).manual_seed(1000 + rank)
     n = N_QUERIES  # per GPU (weak scaling: every rank owns its own index range of a world*n query buffer)
     x = torch.rand((n, 64), device=dev, generator=g).half()
     out = torch.empty((n, 3), device=dev, dtype=torch.float16)
     infer = lambda: st.infer_encoded(x, out, clamp=True)
+    # the scene + the frame's queries in the reference's own format (20-byte NRCEvalRecord per pixel)
+    sa = synth.make_scene_arrays(7, n_prims=20000, n_instances=8, n_materials=64, n_textures=8)
+    scene = nrc.DeviceScene(sa["vertices"], sa["vertex_indices"], sa["texcoords"], sa["texcoord_indices"], sa["materials"],
+                            sa["material_ids"], sa["transforms"], sa["textures"], device=local)
+    ev = synth.eval_records_screen(11 + rank, 1920, 1080, 20000, 8)
+    h_ev = torch.from_numpy(ev.view(np.uint8).reshape(-1)).pin_memory()
+    e2e_steps = max(3, min(K, 20))
 
+    extra, train, multi = {}, {}, {}
     with ClockSampler(local) as clocks:
         ms = timed(infer, K, W)
         value = world * n / (ms * 1e-3)
 
-        # ---- e2e: same call, HOST buffers, copies inside the timed region
+        # ---- e2e (headline): the frame's queries as the reference stores them - 20-byte NRCEvalRecords in pinned HOST memory -
+        # through ONE C-ABI call that returns the radiance per query in host memory; H2D / gather+encode+MLP / D2H pipelined inside
+        hout = torch.empty((n, 3), dtype=torch.float16).pin_memory()
+        ms_e2e = timed(lambda: st.infer_eval_records_host(h_ev, scene, hout), e2e_steps, 3)
+        # ... and the round-1 form of the same number: pre-encoded fp16 inputs (128 B / query) from host memory
         hx = torch.empty((n, 64), dtype=torch.float16).pin_memory()
         hx.copy_(x.cpu())
-        hout = torch.empty((n, 3), dtype=torch.float16).pin_memory()
+        ms_e2e_enc = timed(lambda: st.infer_encoded_host(hx, hout, clamp=True), e2e_steps, 3)
+        extra["e2e_preencoded_queries_per_s"] = world * n / (ms_e2e_enc * 1e-3)
+        extra["e2e_preencoded_ms_per_step"] = ms_e2e_enc
+        extra["e2e_preencoded_h2d_bytes_per_step"] = n * 128
 
-        def e2e_step():  # the C-ABI call on host buffers: chunked H2D / MLP / D2H overlapped inside nrc_infer_encoded_host
-            st.infer_encoded_host(hx, hout, clamp=True)
-        e2e_steps = max(3, min(K, 20))
-        ms_e2e = timed(e2e_step, e2e_steps, 3)
-
-        extra = {}
         if not args.no_extra:
             # fused-encode inference from 56-byte UnpackedNRCInput-shaped records
             rec = torch.rand((n, 14), device=dev, generator=g)
             ms_u = timed(lambda: st.infer_unpacked(rec, outputs=out), max(10, K // 4), 3)
             extra["infer_unpacked_queries_per_s"] = world * n / (ms_u * 1e-3)
             extra["infer_unpacked_ms_per_step"] = ms_u
-            # the reference's own formats: 20-byte NRCEvalRecord per pixel + scene gather (UnpackNRCInput) -> composite into the
-            # rgba32f / rg32f screen images: the exact nrc_inference.comp pass (nrc_infer), from device and from host records
-            from vknrc_b200 import synth
-            sa = synth.make_scene_arrays(7, n_prims=20000, n_instances=8, n_materials=64, n_textures=8)
-            scene = nrc.DeviceScene(sa["vertices"], sa["vertex_indices"], sa["texcoords"], sa["texcoord_indices"], sa["materials"],
-                                    sa["material_ids"], sa["transforms"], sa["textures"], device=local)
-            ev = synth.eval_records_screen(11 + rank, 1920, 1080, 20000, 8)
-            h_ev = torch.from_numpy(ev.view(np.uint8).reshape(-1)).pin_memory()
+            del rec
+            # the exact nrc_inference.comp pass (nrc_infer): 20-byte NRCEvalRecord per pixel + scene gather -> composite into the
+            # rgba32f / rg32f screen images, from device records
             d_ev = h_ev.to(dev)
             d_bf = torch.rand((1080, 1920, 4), device=dev, generator=g)
             d_gb = torch.rand((1080, 1920, 2), device=dev, generator=g)
@@ -261,55 +345,88 @@ def main():
             ms_r = timed(lambda: st.infer(d_ev, cnt, scene, d_bf, d_gb, 1920, d_trs, max_count=n), max(10, K // 4), 3)
             extra["infer_eval_records_scatter_queries_per_s"] = world * n / (ms_r * 1e-3)
             extra["infer_eval_records_scatter_ms_per_step"] = ms_r
-            h_bf = torch.empty((1080, 1920, 4), dtype=torch.float32).pin_memory()
+            extra["infer_eval_records_scatter_tflops_per_gpu"] = n * FLOP_PER_QUERY / (ms_r * 1e-3) / 1e12
+            ms_p = timed(lambda: st.infer_packed(d_ev[4:], scene, outputs=out, stride_bytes=20, max_count=n), max(10, K // 4), 3)
+            extra["infer_eval_records_f16_ms_per_step"] = ms_p
+            del d_bf, d_gb
 
-            def e2e_records():  # host records in, composited image back: 41.5 MB up, 33.2 MB down per frame
-                d_ev.copy_(h_ev, non_blocking=True)
-                st.infer(d_ev, cnt, scene, d_bf, d_gb, 1920, d_trs, max_count=n)
-                h_bf.copy_(d_bf, non_blocking=True)
-            ms_re = timed(e2e_records, max(3, min(K, 20)), 3)
-            extra["e2e_eval_records_queries_per_s"] = world * n / (ms_re * 1e-3)
-            extra["e2e_eval_records_ms_per_step"] = ms_re
-            # training: one frame = 4 dependent batches of 16384 records (configs[3]); records sharded per GPU
+            # ---- training (the other half of the metric). One frame = 4 dependent batches of 16384 records (configs[3]).
             nb = nrc.TRAIN_BATCH_SIZE
             trec = torch.rand((4, nb, 14), device=dev, generator=g)
             ttgt = torch.rand((4, nb, 3), device=dev, generator=g)
-
             trecs, ttgts = [trec[b] for b in range(4)], [ttgt[b] for b in range(4)]
-            if world > 1:
-                st.comm_connect()  # peer-mapped inboxes: the gradient all-reduce runs inside the training kernel
+            exchange = "none (1 GPU)"
+            if world > 1:  # the gradient all-reduce runs inside the training kernel; NVSwitch multicast push when the box has NVLS
+                try:
+                    exchange = "in-kernel, multimem.st over NVSwitch multicast" if st.comm_attach_symmetric() else "in-kernel, unicast stores (symmetric memory, no multicast)"
+                except Exception as e:  # no symmetric memory: CUDA-IPC inboxes
+                    st.comm_connect()
+                    exchange = f"in-kernel, unicast stores over CUDA-IPC inboxes ({type(e).__name__})"
+            multi["exchange"] = exchange
 
-            def train_frame():
-                # the whole frame (4 x [gradient -> reduce -> (NVLink all-reduce) -> Adam]) is ONE cooperative kernel launch
+            def train_frame():  # the whole frame (4 x [gradient -> reduce -> (NVLink all-reduce) -> Adam]) is ONE cooperative kernel launch
                 st.train_frame_unpacked(trecs, ttgts)
-            ms_t = timed(train_frame, max(10, K // 4), 3)
+            ms_t = timed(train_frame, max(40, K // 2), 5)  # (enough frames to amortise the ranks' launch skew of the first one)
             # the same frame on 40-byte NRCTrainRecord buffers (scene gather fused), the reference's NNTrain input
             d_trec = [torch.from_numpy(synth.train_records(100 + 10 * rank + b, nb, 20000, 8).view(np.uint8).reshape(-1)).to(dev) for b in range(4)]
-            ms_tr = timed(lambda: st.train_frame(d_trec, scene, max_count=nb), max(10, K // 4), 3)
-            extra["train_records_frame_ms_4x16384"] = ms_tr
-            extra["train_records_per_s"] = world * 4 * nb / (ms_t * 1e-3)
-            extra["train_ms_per_frame_4x16384"] = ms_t
-            extra["train_tflops"] = world * 4 * nb * FLOP_PER_TRAIN_RECORD / (ms_t * 1e-3) / 1e12
-            # throughput point of the sweep: 2^20 records in one step
+            ms_tr = timed(lambda: st.train_frame(d_trec, scene, max_count=nb), max(40, K // 2), 5)
+            train.update({
+                "records_per_s": world * 4 * nb / (ms_t * 1e-3), "unit": "records/s", "scaling": "weak",
+                "records_per_gpu_per_frame": 4 * nb, "frame_us": ms_t * 1e3, "frame_us_from_train_records": ms_tr * 1e3,
+                "records_per_s_from_train_records": world * 4 * nb / (ms_tr * 1e-3),
+                "tflops_per_gpu": 4 * nb * FLOP_PER_TRAIN_RECORD / (ms_t * 1e-3) / 1e12,
+                "flop_per_record": FLOP_PER_TRAIN_RECORD,
+                "bound": "latency: 4 dependent batches of one 128-record tile per SM, 2 grid barriers + 1 L2 round trip each (DESIGN 3.2)"})
+            # throughput point of the sweep: 2^20 records in one step (per GPU)
             big = 1 << 20
             brec = torch.rand((big, 14), device=dev, generator=g)
             btgt = torch.rand((big, 3), device=dev, generator=g)
+            ms_b = timed(lambda: st.train_batch_unpacked(brec, btgt, write_use_weights=True), 5, 2)
+            tf_b = big * FLOP_PER_TRAIN_RECORD / (ms_b * 1e-3) / 1e12
+            train["step_2p20"] = {"records_per_s": world * big / (ms_b * 1e-3), "us_per_step": ms_b * 1e3, "tflops_per_gpu": tf_b,
+                                  "roofline": {"bound": "tensor", "achieved": tf_b, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tf_b / peaks["tflops"],
+                                               "frac_of_sustained": tf_b / peaks["tflops_sustained"] if peaks["tflops_sustained"] else None}}
+            del brec, btgt
+            if world > 1:
+                # (1) the replicas must be bit-identical after the fused frames: weights, optimizer entries, gradients
+                st.comm_status()
+                d = st.download()
+                blob = np.concatenate([np.ascontiguousarray(d[k]).view(np.uint8).reshape(-1) for k in ("weights", "use_weights", "optimizer_entries", "gradients")])
+                mine = torch.from_numpy(blob).to(dev)
+                allb = [torch.empty_like(mine) for _ in range(world)]
+                dist.all_gather(allb, mine)
+                multi["replicated_bit_identical"] = bool(all(torch.equal(allb[0], b) for b in allb))
+                # (2) fused in-kernel exchange vs gradient -> ncclAllReduce -> nrc_adam_step, both from the same weights on the same shards
+                st_f, st_s = nrc.NrcState(local, (64, 64), seed=77), nrc.NrcState(local, (64, 64), seed=77)
+                try:
+                    st_f.comm_attach_symmetric()
+                except Exception:
+                    st_f.comm_connect()
+                gt = st_s.gradient_tensor()
 
-            def train_big():
-                st.train_batch_unpacked(brec, btgt, write_use_weights=True)
-            ms_b = timed(train_big, 5, 2)
-            if world > 1:  # the stock-collective version of the same frame, for comparison: gradient -> NCCL all-reduce -> Adam
-                st_split = nrc.NrcState(local, (1920, 1080), seed=1234)
-                gt = st_split.gradient_tensor()
-
-                def train_frame_nccl():
+                def split_frame(state=st_s, grad=gt):
                     for b in range(4):
-                        st_split.gradient_unpacked(trec[b], ttgt[b])
-                        dist.all_reduce(gt)  # 20 736 fp32: dW + loss + record count
-                        st_split.adam_step(write_use_weights=(b == 3))
-                extra["train_ms_per_frame_nccl_split"] = timed(train_frame_nccl, max(10, K // 4), 3)
-            extra["train_2p20_records_per_s"] = world * big / (ms_b * 1e-3)
-            extra["train_2p20_tflops_per_gpu"] = big * FLOP_PER_TRAIN_RECORD / (ms_b * 1e-3) / 1e12
+                        state.gradient_unpacked(trecs[b], ttgts[b])
+                        dist.all_reduce(grad)  # 20 736 fp32: dW + loss + record count
+                        state.adam_step(write_use_weights=(b == 3))
+                for _ in range(2):
+                    st_f.train_frame_unpacked(trecs, ttgts)
+                    split_frame()
+                st_f.comm_status()
+                a, b_ = st_f.download(), st_s.download()
+                multi["fused_vs_nccl_split_max_weight_diff"] = float(np.abs(a["weights"].astype(np.float32) - b_["weights"].astype(np.float32)).max())
+                multi["fused_vs_nccl_split_bit_equal"] = bool(np.array_equal(a["optimizer_entries"].view(np.uint32), b_["optimizer_entries"].view(np.uint32)))
+                multi["train_frame_us_nccl_split"] = timed(split_frame, max(40, K // 2), 5) * 1e3
+                multi["train_frame_us_fused_weak"] = ms_t * 1e3
+                # (3) configs[3] as written: ONE global frame of 4 x 16384 records sharded over the GPUs (strong scaling of a
+                # latency-bound frame: reported as measured, it is not expected to speed up)
+                lo, hi = shard_range(nb, rank, world, align=128)
+                srecs, stgts = [trec[b, lo:hi].contiguous() for b in range(4)], [ttgt[b, lo:hi].contiguous() for b in range(4)]
+                ms_s = timed(lambda: st.train_frame_unpacked(srecs, stgts, max_count=hi - lo), max(40, K // 2), 5)
+                multi["train_frame_us_sharded_4x16384_global"] = ms_s * 1e3
+                multi["train_records_per_s_sharded"] = 4 * nb / (ms_s * 1e-3)
+                st.comm_status()
+                st_f.comm_shutdown(), st_f.close(), st_s.close()
 
     if not args.no_extra:
         # The headline number above is a short burst (K launches). On random data this kernel is limited by the 1 kW board
@@ -323,7 +440,6 @@ def main():
         extra["infer_sustained_tflops"] = n * FLOP_PER_QUERY / (ms_sus * 1e-3) / 1e12
         extra["infer_sustained_clocks"] = clocks_sustained.summary()
 
-    peaks = measured_peaks()
     tflops = n * FLOP_PER_QUERY / (ms * 1e-3) / 1e12  # per GPU (the kernel of one rank)
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
@@ -334,16 +450,18 @@ def main():
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
         "config": {"workload": WORKLOAD, "queries_per_gpu_per_step": n, "network": "64->5x(64,ReLU)->3, fp16 weights, fp32 TMEM accumulate",
                    "l2_policy": "inputs (265 MB per step) exceed the 126 MB L2; no flush needed", "parallelism": f"index-range x{world}",
-                   "host_numa_node_rank0": numa},
-        "e2e": {"value": world * n / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 128, "d2h_bytes_per_step": n * 6,
+                   "host_cpu_binding": numa,
+                   "e2e_call": "nrc_infer_eval_records_host: 20-byte NRCEvalRecords (the reference's query format) in pinned host memory -> fp16x3 radiance in host memory"},
+        "e2e": {"value": world * n / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": n * 20, "d2h_bytes_per_step": n * 6,
                 "ms_per_step": ms_e2e},
         "gpu_launches": K,  # one nrc_infer_kernel launch per step inside the timed region
         "clocks": clocks.summary(),
         "roofline": {"bound": "tensor", "achieved": tflops, "peak": peaks["tflops"], "unit": "TFLOP/s", "frac": tflops / peaks["tflops"],
-                     "traffic": traffic, "peak_source": f"{peaks['source']} cuBLAS bf16 burst (sustained {peaks['tflops_sustained']})",
+                     "traffic": traffic, "traffic_source": "profiles/ncu_traffic.json (one ncu --set full capture of this kernel), not measured in this run",
+                     "peak_source": f"{peaks['source']} cuBLAS bf16 burst (sustained {peaks['tflops_sustained']})",
                      "flop_per_query": FLOP_PER_QUERY,
                      "hbm_gbs_achieved": n * BYTES_PER_QUERY / (ms * 1e-3) / 1e9, "hbm_gbs_peak": peaks["hbm_gbs"]},
-        "extra": extra,
+        "train": train, "multi_gpu": multi, "extra": extra,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -353,10 +471,19 @@ def main():
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
                                 "sample": f"{sample} of {N_QUERIES} pre-encoded queries, median of 2 runs, "
                                           f"{'test/main.cpp Evaluate (Eigen fp16) from oracle/_ref' if kind == 'reference' else 'oracle port'}"}
+        trate, tkind, _ = cpu_reference_train_rate(16384, 2, threads)
+        line["cpu_baseline_train"] = {"value": trate, "unit": "records/s", "cores": threads, "kind": tkind,
+                                      "sample": "one 16384-record batch (the paper's batch), median of 2 runs, test/main.cpp Train from oracle/_ref "
+                                                "(a debugging sketch of the backward pass, SURVEY Q13: timed as the reference's CPU cost of a step)"}
+    ok = True
+    if world > 1 and multi and not multi.get("replicated_bit_identical", True):
+        ok = False  # the data-parallel replicas diverged: this run is not a valid measurement
     if rank == 0:
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+    if not ok:
+        sys.exit(3)
 
 
 if __name__ == "__main__":

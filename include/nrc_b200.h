@@ -97,6 +97,11 @@ int nrc_infer_encoded(nrc_handle_t h, const void *d_inputs, void *d_outputs_f16v
  * `stream` completes when the outputs are in `h_outputs`. Pinned host memory makes the copies truly asynchronous. */
 int nrc_infer_encoded_host(nrc_handle_t h, const void *h_inputs, void *h_outputs_f16vec3, uint64_t n, int clamp_output,
                            void *stream);
+/* The reference's own query format from HOST memory: `n` 20-byte NRCEvalRecords (the buffer path_tracer.comp fills, binding 8 of
+ * nrc_inference.comp; `dst` is ignored) -> UnpackNRCInput + encode + MLP with use_weights -> max(y, 0) as fp16 x 3 per query in
+ * `h_outputs`, same chunked three-stream pipeline: 20 bytes per query travel up and 6 down instead of 128 + 6. */
+int nrc_infer_eval_records_host(nrc_handle_t h, const void *h_eval_records, uint64_t n, const NrcScene *scene,
+                                void *h_outputs_f16vec3, void *stream);
 /* records = 14 fp32 each (UnpackedNRCInput order, NRCRecord.glsl:40-45) `stride_bytes` apart; outputs max(y,0) fp16x3 */
 int nrc_infer_unpacked(nrc_handle_t h, const void *d_records, uint32_t stride_bytes, const uint32_t *d_count,
                        uint64_t max_count, void *d_outputs_f16vec3, void *stream);

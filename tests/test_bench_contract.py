@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 def test_reference_arm_prints_one_contract_line():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "2", "--warmup", "1"],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+                       capture_output=True, text=True, timeout=600, cwd=ROOT, env=dict(os.environ, NRC_BENCH_REF_QUERIES="32768"))
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1, r.stdout
@@ -20,6 +20,8 @@ def test_reference_arm_prints_one_contract_line():
     assert d["config"]["workload"] == "nrc_inference_1080p_preencoded"
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["same_config"] is False and d["config"]["queries_per_step"] == 32768  # (this test shrinks the frame; the default is the whole frame)
+    assert d["cpu_baseline_train"]["unit"] == "records/s" and d["cpu_baseline_train"]["value"] > 0  # the reference's CPU Train, timed beside Evaluate
 
 
 def test_reference_arm_other_ranks_exit_quietly():

@@ -556,3 +556,24 @@ def test_training_calls_replay_correctly_from_a_cuda_graph(nrc, state):
     assert np.array_equal(direct["optimizer_entries"].view(np.uint32), replayed["optimizer_entries"].view(np.uint32))
     assert direct["optimizer_state"] == replayed["optimizer_state"] and replayed["optimizer_state"]["t"] == 12
     assert torch.equal(y, state.infer_encoded(x, clamp=True))  # the captured inference ran on the weights of the third replay
+
+
+def test_infer_eval_records_host_equals_device_path(nrc):
+    """nrc_infer_eval_records_host (20-byte NRCEvalRecords in host memory -> fp16x3 in host memory, chunked three-stream pipeline)
+    must equal nrc_infer_packed on device copies of the same records bit for bit, also for a ragged size and a second call that
+    reuses the staging buffers."""
+    from util import make_scene
+    from vknrc_b200 import synth
+    sc = make_scene(33)
+    dsc = nrc.DeviceScene(sc.vertices, sc.vertex_indices, sc.texcoords, sc.texcoord_indices, sc.materials, sc.material_ids, sc.transforms, sc.textures)
+    st = nrc.NrcState(0, (64, 64), seed=9)
+    for n in (70001, 5000):
+        ev = synth.eval_records_screen(34, n, 1, sc.material_ids.shape[0], sc.transforms.shape[0])
+        h_ev = torch.from_numpy(ev.view(np.uint8).reshape(-1)).pin_memory()
+        h_out = torch.empty((n, 3), dtype=torch.float16).pin_memory()
+        st.infer_eval_records_host(h_ev, dsc, h_out)
+        torch.cuda.synchronize()
+        d_ev = h_ev.cuda()
+        ref = st.infer_packed(d_ev[4:], dsc, stride_bytes=20, max_count=n).cpu()
+        assert torch.equal(h_out, ref)
+    st.close()

@@ -154,6 +154,7 @@ SIGNATURES = {
     "nrc_image_train_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                        C.c_float, C.c_void_p]),
     "nrc_infer_encoded_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_int, C.c_void_p]),
+    "nrc_infer_eval_records_host": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrc_scene_prim_table_bytes": (C.c_uint64, [C.c_uint32]),
     "nrc_scene_build_prim_table": (C.c_int, [C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "nrc_image_infer": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p]),
@@ -175,7 +176,12 @@ def lib() -> C.CDLL:
             raise NrcError(f"{LIB_PATH} is missing: run `python -m vknrc_b200.build` (needs nvcc). There is no CPU fallback.")
         L = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
-            fn = getattr(L, name)
+            try:
+                fn = getattr(L, name)
+            except AttributeError:
+                if os.environ.get("NRC_B200_LIB"):  # an older development build timed beside the current one (tools/lab_train.py)
+                    continue
+                raise
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
@@ -334,6 +340,13 @@ class NrcState:
         assert not h_inputs.is_cuda and not h_outputs.is_cuda and h_inputs.is_contiguous() and h_outputs.is_contiguous()
         n = h_inputs.shape[0]
         _check(lib().nrc_infer_encoded_host(self._h, h_inputs.data_ptr(), h_outputs.data_ptr(), n, int(clamp), _stream()))
+        return h_outputs
+
+    def infer_eval_records_host(self, h_eval_records, scene: "DeviceScene", h_outputs):
+        """nrc_infer_eval_records_host: 20-byte NRCEvalRecords in (pinned) HOST memory -> fp16 x 3 radiance per query in host memory."""
+        assert not h_eval_records.is_cuda and not h_outputs.is_cuda and h_eval_records.is_contiguous() and h_outputs.is_contiguous()
+        n = h_eval_records.numel() * h_eval_records.element_size() // 20
+        _check(lib().nrc_infer_eval_records_host(self._h, h_eval_records.data_ptr(), n, C.byref(scene.c), h_outputs.data_ptr(), _stream()))
         return h_outputs
 
     def infer_unpacked(self, records, count=None, outputs=None, stride_bytes: int = 56, max_count=None):

@@ -313,10 +313,13 @@ int NrcState::Infer(InferParams p, const void *encoded_inputs, const __half *wei
 	return NRC_OK;
 }
 
-int NrcState::InferEncodedHost(const void *h_inputs, void *h_outputs, uint64_t n, int clamp_output, const __half *weights, cudaStream_t stream) {
+// Host-buffer inference: the queries are cut in chunks of whole tiles; chunk c's host -> device copy, MLP launch and
+// device -> host copy run on three streams (both copy engines + the SMs busy at once), ordered after what `stream` holds at
+// the call; `stream` completes when the last outputs are on the host. `launch_chunk(first, count, d_in, d_out)` enqueues the
+// kernel of one chunk on `stream`.
+template <class LaunchChunk>
+int NrcState::host_pipeline(const void *h_in, uint32_t in_bytes, void *h_out, uint32_t out_bytes, uint64_t n, cudaStream_t stream, LaunchChunk launch_chunk) {
 	auto sink = [&](int c, const std::string &s) { return fail(c, s); };
-	if (n == 0)
-		return NRC_OK;
 	NRC_CUDA_TRY(cudaSetDevice(m_device), sink);
 	if (!m_stream_in) {
 		NRC_CUDA_TRY(cudaStreamCreateWithFlags(&m_stream_in, cudaStreamNonBlocking), sink);
@@ -328,19 +331,14 @@ int NrcState::InferEncodedHost(const void *h_inputs, void *h_outputs, uint64_t n
 			NRC_CUDA_TRY(cudaEventCreateWithFlags(&m_ev_done[c], cudaEventDisableTiming), sink);
 		}
 	}
-	if (n > m_stage_capacity) { // (re-allocation synchronises the device: a one-time cost per size)
+	if (n * in_bytes > m_stage_in_bytes || n * out_bytes > m_stage_out_bytes) { // (re-allocation synchronises the device: a one-time cost per size)
 		cudaFree(m_stage_in), cudaFree(m_stage_out);
-		m_stage_in = m_stage_out = nullptr, m_stage_capacity = 0;
+		m_stage_in = m_stage_out = nullptr, m_stage_in_bytes = m_stage_out_bytes = 0;
 		m_maps.clear(); // (descriptors of the freed staging buffer must not outlive it)
-		NRC_CUDA_TRY(cudaMalloc(&m_stage_in, n * 128), sink);
-		NRC_CUDA_TRY(cudaMalloc(&m_stage_out, n * 6), sink);
-		m_stage_capacity = n;
+		NRC_CUDA_TRY(cudaMalloc(&m_stage_in, n * in_bytes), sink);
+		NRC_CUDA_TRY(cudaMalloc(&m_stage_out, n * out_bytes), sink);
+		m_stage_in_bytes = n * in_bytes, m_stage_out_bytes = n * out_bytes;
 	}
-	CUtensorMap tm_w, tm_in;
-	std::string err;
-	int rc = cached_map(&tm_w, weights, NRC_WEIGHT_ROWS, 64, &err);
-	if (rc != NRC_OK)
-		return fail(rc, err);
 	// equal chunks of whole 128-query tiles (the host -> device copies are the long pole: everything else hides under them)
 	const uint64_t tiles = (n + NRC_TILE - 1) / NRC_TILE;
 	const int chunks = (int)(tiles < (uint64_t)kHostChunks ? tiles : (uint64_t)kHostChunks);
@@ -351,23 +349,44 @@ int NrcState::InferEncodedHost(const void *h_inputs, void *h_outputs, uint64_t n
 	for (int c = 0; c < chunks; ++c) {
 		const uint64_t last_tile = tiles * (uint64_t)(c + 1) / (uint64_t)chunks;
 		const uint64_t end = last_tile * NRC_TILE < n ? last_tile * NRC_TILE : n, cnt = end - first;
-		NRC_CUDA_TRY(cudaMemcpyAsync((uint8_t *)m_stage_in + first * 128, (const uint8_t *)h_inputs + first * 128, cnt * 128, cudaMemcpyHostToDevice, m_stream_in), sink);
+		uint8_t *d_in = (uint8_t *)m_stage_in + first * in_bytes, *d_out = (uint8_t *)m_stage_out + first * out_bytes;
+		NRC_CUDA_TRY(cudaMemcpyAsync(d_in, (const uint8_t *)h_in + first * in_bytes, cnt * in_bytes, cudaMemcpyHostToDevice, m_stream_in), sink);
 		NRC_CUDA_TRY(cudaEventRecord(m_ev_in[c], m_stream_in), sink);
 		NRC_CUDA_TRY(cudaStreamWaitEvent(stream, m_ev_in[c], 0), sink);
-		InferParams p{};
-		p.n = cnt, p.in_mode = NRC_IN_ENCODED, p.out_mode = NRC_OUT_F16VEC3, p.clamp_output = clamp_output, p.out = (uint8_t *)m_stage_out + first * 6;
-		rc = cached_map(&tm_in, (const uint8_t *)m_stage_in + first * 128, cnt, NRC_TILE, &err);
-		if (rc != NRC_OK)
-			return fail(rc, err);
-		NRC_CUDA_TRY(launch_infer(p, tm_w, tm_in, m_sms, stream), sink);
+		if (int rc = launch_chunk(first, cnt, d_in, d_out); rc != NRC_OK)
+			return rc;
 		NRC_CUDA_TRY(cudaEventRecord(m_ev_done[c], stream), sink);
 		NRC_CUDA_TRY(cudaStreamWaitEvent(m_stream_out, m_ev_done[c], 0), sink);
-		NRC_CUDA_TRY(cudaMemcpyAsync((uint8_t *)h_outputs + first * 6, (const uint8_t *)m_stage_out + first * 6, cnt * 6, cudaMemcpyDeviceToHost, m_stream_out), sink);
+		NRC_CUDA_TRY(cudaMemcpyAsync((uint8_t *)h_out + first * out_bytes, d_out, cnt * out_bytes, cudaMemcpyDeviceToHost, m_stream_out), sink);
 		first = end;
 	}
 	NRC_CUDA_TRY(cudaEventRecord(m_ev_out, m_stream_out), sink);
 	NRC_CUDA_TRY(cudaStreamWaitEvent(stream, m_ev_out, 0), sink); // `stream` completes when the last outputs are on the host
 	return NRC_OK;
+}
+
+int NrcState::InferEncodedHost(const void *h_inputs, void *h_outputs, uint64_t n, int clamp_output, const __half *weights, cudaStream_t stream) {
+	if (n == 0)
+		return NRC_OK;
+	return host_pipeline(h_inputs, 128, h_outputs, 6, n, stream, [&](uint64_t, uint64_t cnt, void *d_in, void *d_out) {
+		InferParams p{};
+		p.n = cnt, p.in_mode = NRC_IN_ENCODED, p.out_mode = NRC_OUT_F16VEC3, p.clamp_output = clamp_output, p.out = d_out;
+		return Infer(p, d_in, weights, stream);
+	});
+}
+
+// The same pipeline for the reference's own query format: 20-byte NRCEvalRecords (or bare 16-byte PackedNRCInputs) in host
+// memory -> UnpackNRCInput + encode + MLP on the device -> max(y, 0) as fp16 x 3 per query back in host memory.
+int NrcState::InferPackedHost(const void *h_records, uint32_t stride_bytes, uint32_t input_offset, void *h_outputs, uint64_t n, const NrcScene &scene,
+                              const __half *weights, cudaStream_t stream) {
+	if (n == 0)
+		return NRC_OK;
+	return host_pipeline(h_records, stride_bytes, h_outputs, 6, n, stream, [&](uint64_t, uint64_t cnt, void *d_in, void *d_out) {
+		InferParams p{};
+		p.n = cnt, p.in_mode = NRC_IN_PACKED, p.out_mode = NRC_OUT_F16VEC3, p.clamp_output = 1;
+		p.in = (const uint8_t *)d_in + input_offset, p.in_stride_bytes = stride_bytes, p.scene = scene, p.out = d_out;
+		return Infer(p, nullptr, weights, stream);
+	});
 }
 
 int NrcState::Train(TrainParams tp, const void *encoded_inputs, const __half *weights, cudaStream_t stream) {
@@ -600,6 +619,8 @@ int nrc_infer_encoded_host(nrc_handle_t h, const void *h_inputs, void *h_outputs
 	return h->state.InferEncodedHost(h_inputs, h_outputs, n, clamp_output, h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
 }
 
+int nrc_infer_eval_records_host(nrc_handle_t h, const void *h_eval_records, uint64_t n, const NrcScene *scene, void *h_outputs, void *stream);
+
 int nrc_infer_unpacked(nrc_handle_t h, const void *d_records, uint32_t stride_bytes, const uint32_t *d_count, uint64_t max_count,
                        void *d_out, void *stream) {
 	NRC_REQUIRE(h, "null handle");
@@ -678,6 +699,18 @@ int nrc_infer_packed(nrc_handle_t h, const void *d_packed_inputs, uint32_t strid
 	p.n = max_count, p.d_count = d_count, p.in_mode = NRC_IN_PACKED, p.out_mode = NRC_OUT_F16VEC3, p.clamp_output = 1;
 	p.in = d_packed_inputs, p.in_stride_bytes = stride_bytes, p.scene = *scene, p.out = d_out;
 	return h->state.Infer(p, nullptr, h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
+}
+
+int nrc_infer_eval_records_host(nrc_handle_t h, const void *h_eval_records, uint64_t n, const NrcScene *scene, void *h_outputs, void *stream) {
+	NRC_REQUIRE(h, "null handle");
+	if (n == 0)
+		return NRC_OK;
+	NRC_REQUIRE(h_eval_records && h_outputs, "nrc_infer_eval_records_host: null buffer");
+	int rc = check_scene(scene);
+	if (rc != NRC_OK)
+		return rc;
+	return h->state.InferPackedHost(h_eval_records, sizeof(NrcEvalRecord), offsetof(NrcEvalRecord, packed_input), h_outputs, n, *scene,
+	                                h->state.GetUseWeightBuffer(), (cudaStream_t)stream);
 }
 
 uint64_t nrc_scene_prim_table_bytes(uint32_t prim_count) { return (uint64_t)prim_count * sizeof(NrcPrimRow); }

@@ -71,6 +71,9 @@ public:
 	// device -> host (test/main.cpp:103-128) - as ONE call on host buffers: the queries are cut in chunks and the three
 	// stages run on three streams (both copy engines + the SMs busy at once), ordered after / before `stream`.
 	int InferEncodedHost(const void *h_inputs, void *h_outputs, uint64_t n, int clamp_output, const __half *weights, cudaStream_t stream);
+	// ... and for host arrays of the reference's query records (PackedNRCInput at `input_offset` of every `stride_bytes`)
+	int InferPackedHost(const void *h_records, uint32_t stride_bytes, uint32_t input_offset, void *h_outputs, uint64_t n, const NrcScene &scene,
+	                    const __half *weights, cudaStream_t stream);
 	// One cooperative launch of nrc_train_kernel: tp.batch[0..num_batches) (inputs / targets / counts / loss), tp.adam_mode,
 	// tp.accumulate / limit / batch_cap and tp.gradients are the caller's; partials, barrier words and the optimizer
 	// buffers are filled in here. `weights` is the fp16 buffer the forward / backward passes read.
@@ -95,6 +98,8 @@ public:
 private:
 	int fail(int code, const std::string &what);
 	int upload_initial(const float *fp32_weights);
+	template <class LaunchChunk>
+	int host_pipeline(const void *h_in, uint32_t in_bytes, void *h_out, uint32_t out_bytes, uint64_t n, cudaStream_t stream, LaunchChunk launch_chunk);
 	int cached_map(CUtensorMap *tm, const void *base, uint64_t rows, uint32_t box_rows, std::string *err);
 	struct MapEntry {
 		const void *base;
@@ -124,7 +129,7 @@ private:
 	// host-buffer path: device staging (grown on demand), copy-in / copy-out streams, per-chunk events
 	static constexpr int kHostChunks = 8;
 	void *m_stage_in{nullptr}, *m_stage_out{nullptr};
-	uint64_t m_stage_capacity{0};
+	uint64_t m_stage_in_bytes{0}, m_stage_out_bytes{0};
 	cudaStream_t m_stream_in{nullptr}, m_stream_out{nullptr};
 	cudaEvent_t m_ev_start{nullptr}, m_ev_in[kHostChunks]{}, m_ev_done[kHostChunks]{}, m_ev_out{nullptr};
 

@@ -47,6 +47,13 @@ __device__ unsigned int g_nrc_gtrace_n;
 #define NRC_GTRACE(tag)
 #endif
 
+#ifndef NRC_COMM_POLL_PARALLEL
+#define NRC_COMM_POLL_PARALLEL 0
+#endif
+#ifndef NRC_TRAIN_TS
+#define NRC_TRAIN_TS 0
+#endif
+
 namespace nrc {
 
 namespace {
@@ -56,8 +63,21 @@ constexpr uint32_t kPoolOff = NRC_LAYERS * 8192;      // P x 16 KB activation ti
                                                       // footprint leaves the L1 32 KB more, which the latency-bound frame feels (-2 us)
 // then 2 x 16 KB deltas (ping-pong: delta_l lives in buffer (5 - l) & 1), then the barriers
 constexpr uint32_t train_smem_bytes(uint32_t pool_tiles) { return kPoolOff + (pool_tiles + 2) * 16384 + 256 + 1024; }
+#if NRC_TRAIN_TS
+// TMEM map (columns x lanes): the M=64 dW accumulators occupy 16 of every 32 lanes, so two of them share 64 columns - dW_l at
+// columns 64*(l/2), lane offset 16*(l%2) (dW_4 with dW_5^T) - 192 columns instead of 336. That leaves room for the fp16 A
+// operands of both streams in TMEM: forward (a_k) and back-propagation (delta_l) run TS-form, 32 instead of 50.8 cycles per
+// MMA, and - more important - the next MMA of a stream only waits for a tcgen05.st, not for shared-memory stores + proxy fence.
+constexpr uint32_t kColWorkF = 192, kColWorkB = 256;  // working accumulators of the forward / backward stream
+constexpr uint32_t kColAF = 320, kColAB = 352;        // fp16 A operands (32 columns = 64 fp16 per lane): a_k / delta_l
+__device__ __forceinline__ constexpr uint32_t dw_col(int l) { return l == 5 ? 128u : 64u * (uint32_t)(l >> 1); }
+__device__ __forceinline__ constexpr uint32_t dw_lane(int l) { return l == 5 ? 16u : 16u * (uint32_t)(l & 1); }
+#else
 constexpr uint32_t kColDW5 = 320;                     // TMEM columns: dW_l at 64*l, dW_5^T at 320,
 constexpr uint32_t kColWorkF = 384, kColWorkB = 448;  // working accumulators of the forward / backward stream
+__device__ __forceinline__ constexpr uint32_t dw_col(int l) { return l == 5 ? kColDW5 : 64u * (uint32_t)l; }
+__device__ __forceinline__ constexpr uint32_t dw_lane(int) { return 0u; }
+#endif
 constexpr uint32_t kEpiWarps = 8, kEpiThreads = 256, kIssueWarp = 8;
 constexpr int kTrainThreads = 288;
 constexpr uint32_t kReduceBlocks = NRC_GRAD_STRIDE / 64; // the reduction works on blocks of 64 consecutive floats
@@ -190,6 +210,84 @@ __device__ __forceinline__ uint32_t wait_peer(const uint64_t *p, uint32_t epoch,
 	}
 	return 0u;
 }
+// The all-reduce over NVLink, fused into the reduction phase: push {epoch, value} words into every peer's inbox (one multicast
+// store through the switch, or one store per peer), spin on the peers' words in the local inbox, add in rank order (identical
+// operands in identical order on every rank => bit-identical sums). Only the MULTI instantiations of the kernel contain it: its
+// registers must not weigh on the single-GPU path (+6 us per frame when they did). Returns true if this CTA gave up waiting for a peer.
+__device__ __forceinline__ bool exchange_with_peers(const CommParams &comm, uint32_t epoch, bool mine_blk, uint32_t my_i, float count, bool &have_peer_counts,
+                                                 uint32_t *peer_counts, float &sum, float &total_count) {
+	const uint32_t world = comm.world, me = comm.rank, parity = epoch & 1u;
+	const size_t dslot = (size_t)parity * NRC_MAX_RANKS * NRC_GRAD_STRIDE, cslot = kCommDataWords + (size_t)parity * NRC_MAX_RANKS;
+	const uint64_t tag = (uint64_t)epoch << 32;
+	bool timed_out = false;
+	if (mine_blk) {
+		const size_t at = dslot + (size_t)me * NRC_GRAD_STRIDE + my_i;
+		if (comm.multicast) {
+			st_multicast(comm.multicast + at, tag | __float_as_uint(sum));
+		} else {
+			for (uint32_t r = 0; r < world; ++r)
+				if (r != me)
+					st_peer(comm.inbox[r] + at, tag | __float_as_uint(sum));
+		}
+	}
+	if (!have_peer_counts && threadIdx.x >= 192 && threadIdx.x < 192 + NRC_MAX_RANKS) { // one thread per peer: the record counts
+		const uint32_t r = threadIdx.x - 192;
+		if (blockIdx.x == 0) { // this rank's count: one word per source, published once per batch by CTA 0
+			if (comm.multicast) {
+				if (r == me)
+					st_multicast(comm.multicast + cslot + me, tag | __float_as_uint(count));
+			} else if (r < world && r != me) {
+				st_peer(comm.inbox[r] + cslot + me, tag | __float_as_uint(count));
+			}
+		}
+		peer_counts[r] = r < world && r != me ? wait_peer(comm.inbox[me] + cslot + r, epoch, comm, timed_out) : 0u;
+	}
+	if (mine_blk) {
+#if NRC_COMM_POLL_PARALLEL
+		// all peers' words requested at once and polled together, then added in rank order. Measured at 8 GPUs: no faster than
+		// waiting for the peers one after the other (88.5 us per frame either way - the words of a 128-byte line arrive together,
+		// so after the first wait the others hit), and 16 more live registers: off by default.
+		const uint64_t *src = comm.inbox[me] + dslot + my_i;
+		uint32_t val[NRC_MAX_RANKS];
+		uint32_t pending = ((1u << world) - 1u) & ~(1u << me);
+		for (uint32_t spins = 0; pending && !timed_out; ++spins) {
+			uint64_t got[NRC_MAX_RANKS];
+#pragma unroll
+			for (uint32_t r = 0; r < NRC_MAX_RANKS; ++r)
+				if (pending >> r & 1u)
+					asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got[r]) : "l"(src + (size_t)r * NRC_GRAD_STRIDE) : "memory");
+#pragma unroll
+			for (uint32_t r = 0; r < NRC_MAX_RANKS; ++r)
+				if ((pending >> r & 1u) && (uint32_t)(got[r] >> 32) == epoch)
+					val[r] = (uint32_t)got[r], pending &= ~(1u << r);
+			if (pending && spins > comm.spin_limit) {
+				timed_out = true;
+				atomicExch(comm.error_word, 1u);
+			}
+			if (pending && spins > 16)
+				__nanosleep(32);
+		}
+		float tot = 0.0f;
+#pragma unroll
+		for (uint32_t r = 0; r < NRC_MAX_RANKS; ++r)
+			if (r < world)
+				tot += r == me ? sum : (pending >> r & 1u) ? 0.0f : __uint_as_float(val[r]);
+		sum = tot;
+#else
+		float tot = 0.0f;
+		for (uint32_t r = 0; r < world; ++r)
+			tot += r == me ? sum : __uint_as_float(wait_peer(comm.inbox[me] + dslot + (size_t)r * NRC_GRAD_STRIDE + my_i, epoch, comm, timed_out));
+		sum = tot;
+#endif
+	}
+	const bool cta_timed_out = __syncthreads_or(timed_out ? 1 : 0) != 0;
+	have_peer_counts = true;
+	total_count = 0.0f;
+	for (uint32_t r = 0; r < world; ++r)
+		total_count += r == me ? count : __uint_as_float(peer_counts[r]); // integers < 2^24: exact
+	return cta_timed_out;
+}
+
 __device__ __forceinline__ float4 ld_cg4(const float *p) {
 	float4 v;
 	asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -197,9 +295,9 @@ __device__ __forceinline__ float4 ld_cg4(const float *p) {
 }
 
 // (168 registers: the register file is per SM sub-partition, 16384 each, and one of the four hosts 3 of the 9 warps)
-template <int IN_MODE>
+template <int IN_MODE, bool MULTI>
 __global__ void __launch_bounds__(kTrainThreads, 1)
-    nrc_train_kernel(const TrainParams tp, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_in) {
+    nrc_train_kernel(const __grid_constant__ TrainParams tp, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_in) {
 	extern __shared__ uint8_t smem_raw[];
 	__shared__ float4 red_sm[3][16][16]; // reduction scratch: [block of the round][partial group][16 x float4 = 64 floats]
 	__shared__ float scratch[16];
@@ -208,8 +306,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	uint8_t *w_sm = smem + kWOff, *pool_sm = smem + kPoolOff, *delta_sm = pool_sm + tp.pool_tiles * 16384;
 	uint64_t *bars = (uint64_t *)(delta_sm + 2 * 16384);
 	uint64_t *w_full = bars, *in_full = bars + 1, *df_full = bars + 2, *db_full = bars + 3, *dw1_done = bars + 4, *tile_done = bars + 5;
-	uint64_t *af_ready = bars + 6, *ab_ready = bars + 7, *d5_ready = bars + 8, *w_ready = bars + 9;
-	uint32_t *tmem_slot = (uint32_t *)(bars + 10);
+	uint64_t *af_ready = bars + 6, *ab_ready = bars + 7, *d5_ready = bars + 8, *w_ready = bars + 9, *ds_ready = bars + 10;
+	uint32_t *tmem_slot = (uint32_t *)(bars + 11);
 #ifdef NRC_TRACE
 	__shared__ uint2 gtrace[NRC_GTRACE_CAP];
 	uint32_t gtrace_n = 0;
@@ -224,6 +322,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	if (threadIdx.x == 0) {
 		mbar_init(w_full, 1), mbar_init(in_full, 1), mbar_init(df_full, 1), mbar_init(db_full, 1), mbar_init(dw1_done, 1), mbar_init(tile_done, 1);
 		mbar_init(af_ready, kEpiWarps), mbar_init(ab_ready, kEpiWarps), mbar_init(d5_ready, kEpiWarps), mbar_init(w_ready, kEpiWarps);
+		mbar_init(ds_ready, kEpiWarps);
 		fence_mbar_init();
 	}
 	if (warp == kIssueWarp)
@@ -245,10 +344,25 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	constexpr uint32_t dhi = kSmemDescHiSw128;
 	const uint32_t df_issue = tmem + kColWorkF, db_issue = tmem + kColWorkB; // issuer's view of the two working accumulators
 	const uint32_t df_mine = tmem_addr(tmem, q * 32, kColWorkF + 32 * h), db_mine = tmem_addr(tmem, q * 32, kColWorkB + 32 * h);
+#if NRC_TRAIN_TS
+	const uint32_t af_issue = tmem + kColAF, ab_issue = tmem + kColAB;           // issuer's view of the two TMEM A operands
+	const uint32_t af_mine = tmem_addr(tmem, q * 32, kColAF + 16 * h), ab_mine = tmem_addr(tmem, q * 32, kColAB + 16 * h); // this thread's half row
+	// operand stored in TENSOR memory + accumulator drained -> one arrival per warp (no shared-memory traffic on this path)
+	auto arrive_tmem = [&](uint64_t *bar) {
+		tc_wait_st();
+		tc_fence_before();
+		__syncwarp();
+		if (lane == 0)
+			mbar_arrive(bar);
+	};
+#endif
 
 	// operand stored (generic-proxy smem writes fenced to the async proxy) + accumulator drained -> one arrival per warp
 	auto arrive_ready = [&](uint64_t *bar) {
 		fence_proxy_async_smem();
+#if NRC_TRAIN_TS
+		tc_wait_st();
+#endif
 		tc_fence_before();
 		__syncwarp();
 		if (lane == 0)
@@ -295,6 +409,9 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			if (valid)
 				encode_oneblob32_half(sc * (float)(h ? py : px), o);
 		}
+#if NRC_TRAIN_TS
+		tmem_st_x16(af_mine, o); // a_0 is also the forward stream's first TMEM operand (completion: tc_wait_st in arrive_ready below)
+#endif
 		store_half_row(dst_tile, o);
 	};
 	auto batch_count = [&](const GradParams &bp) -> uint64_t { // nrc_train_prepare.comp:17-18: count = min(count, capacity)
@@ -318,6 +435,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	// reading a_1, whose buffer the next TMA input tile overwrites.
 	uint32_t df_ph = 0, db_ph = 0;            // epilogue threads
 	uint32_t af_ph = 0, ab_ph = 0, d5_ph = 0; // issuer
+	uint32_t ds_ph = 0;                       // issuer (TS form): delta_l is also in shared memory (dW_l's operand)
 	uint32_t in_ph = 0, dw1_ph = 0;           // issuer: TMA input tiles, dw1_done
 	uint32_t done_ph = 0;                     // epilogue threads: tile_done completes once per batch in which the CTA had tiles
 
@@ -330,10 +448,17 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		encode_tile_row(tp.batch[0], n, blockIdx.x, pool_sm);
 		arrive_ready(af_ready);
 	}
+	if (my_tiles == 0 && warp < kEpiWarps) {
+		// A CTA without a tile in batch 0 never issues the TMA weight load whose out-of-bounds fill pads W_5 from 3 to 64 rows
+		// (rows 323..383 of the weight tile): it writes those zeros itself, once. The same threads stage the weights in the
+		// first batch where the CTA has work, and their proxy fence there also covers these stores.
+		for (uint32_t idx = NRC_WEIGHT_ROWS * 8 + threadIdx.x; idx < NRC_LAYERS * 64 * 8; idx += kEpiThreads)
+			*(uint4 *)(w_sm + (idx >> 3) * 128 + (((idx & 7u) ^ ((idx >> 3) & 7u)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
+	}
 	uint32_t w_reloads = 0; // weight re-stagings by the epilogue warps so far (w_ready phase)
 	uint32_t bar_target = *(volatile const uint32_t *)(tp.grid_bar + 1); // (meaningful in thread 0 only)
 	// multi-GPU: the epoch of this launch's first exchange, also device-resident (advanced by CTA 0 below)
-	const uint32_t epoch_base = tp.comm.world > 1 ? *(volatile const uint32_t *)tp.comm.epoch_word + 1u : 0u;
+	const uint32_t epoch_base = MULTI && tp.comm.world > 1 ? *(volatile const uint32_t *)tp.comm.epoch_word + 1u : 0u;
 
 #pragma unroll 1
 	for (uint32_t b = 0; b < tp.num_batches; ++b) {
@@ -349,22 +474,20 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		if (b > 0 && my_tiles && warp < kEpiWarps) {
 			// Re-stage the weights the previous batch's optimizer phase just wrote (by other SMs; the grid barrier made them
 			// visible in L2): plain 16-byte L2 loads into the swizzled tile, no global cross-proxy fence needed. Rows past 323
-			// are written as zeros (what TMA's out-of-bounds fill does in batch 0).
+			// hold zeros: from TMA's out-of-bounds fill in batch 0, or written in the prologue by a CTA without a tile in batch 0.
 			const uint4 *src = (const uint4 *)tp.adam.weights;
-			constexpr int kChunks = NRC_LAYERS * 64 * 8;                         // 16-byte chunks of the 384-row tile
-			constexpr int kPerThread = (kChunks + kEpiThreads - 1) / kEpiThreads; // 12: every load in flight at once
+			constexpr int kPerThread = (NRC_WEIGHT_ROWS * 8 + kEpiThreads - 1) / kEpiThreads; // 11: every load in flight at once
 			uint4 v[kPerThread];
 #pragma unroll
 			for (int u = 0; u < kPerThread; ++u) {
 				const uint32_t idx = threadIdx.x + u * kEpiThreads;
-				v[u] = make_uint4(0u, 0u, 0u, 0u); // rows 323..383 pad W_5 with zeros: a CTA that had no tile in batch 0 never ran the TMA load
 				if (idx < NRC_WEIGHT_ROWS * 8)
 					asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v[u].x), "=r"(v[u].y), "=r"(v[u].z), "=r"(v[u].w) : "l"(src + idx));
 			}
 #pragma unroll
 			for (int u = 0; u < kPerThread; ++u) {
 				const uint32_t idx = threadIdx.x + u * kEpiThreads, r = idx >> 3, c = idx & 7u;
-				if (idx < (uint32_t)kChunks)
+				if (idx < NRC_WEIGHT_ROWS * 8)
 					*(uint4 *)(w_sm + r * 128 + ((c ^ (r & 7u)) << 4)) = v[u];
 			}
 			fence_proxy_async_smem();
@@ -437,9 +560,18 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							}
 							tc_fence_after();
 							const uint32_t a_d = pool_desc + fw[k] * (16384 >> 4), b_d = w_desc + (uint32_t)(k * (8192 >> 4));
+#if NRC_TRAIN_TS
+							if (!(IN_MODE == NRC_IN_ENCODED && k == 0)) { // a_k from tensor memory (pre-encoded a_0 arrives in shared memory by TMA)
 #pragma unroll
-							for (int kk = 0; kk < 4; ++kk)
-								mma_ss_lh(df_issue, a_d + kk * 2, b_d + kk * 2, dhi, k < 5 ? id_fwd64 : id_fwd16, kk > 0);
+								for (int kk = 0; kk < 4; ++kk)
+									mma_ts_lh(df_issue, af_issue + kk * 8, b_d + kk * 2, dhi, k < 5 ? id_fwd64 : id_fwd16, kk > 0);
+							} else
+#endif
+							{
+#pragma unroll
+								for (int kk = 0; kk < 4; ++kk)
+									mma_ss_lh(df_issue, a_d + kk * 2, b_d + kk * 2, dhi, k < 5 ? id_fwd64 : id_fwd16, kk > 0);
+							}
 							tc_commit(df_full);
 						}
 						if (has_b) { // ---- backward layer l of tile r - 1: dA first (critical path), then dW_l
@@ -451,22 +583,41 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							const uint32_t dl = del_desc + (uint32_t)(((5 - l) & 1) * (16384 >> 4));
 							const uint32_t al = pool_desc + bw[l] * (16384 >> 4), wl = w_desc + (uint32_t)(l * (8192 >> 4));
 							const uint32_t acc = (r > 1) ? 1u : 0u; // dW accumulates from the CTA's second tile on
+							const uint32_t dw_acc = tmem_addr(tmem, dw_lane(l), dw_col(l)); // dW_l's accumulator
 							if (l == 5) {
+#if NRC_TRAIN_TS
+								mma_ts_lh(db_issue, ab_issue, wl, dhi, id_da, 0);
+								tc_commit(db_full);
+								mbar_wait(ds_ready, ds_ph); // delta_5 has reached shared memory too
+								ds_ph ^= 1;
+								tc_fence_after();
+#else
 								mma_ss_lh(db_issue, dl, wl, dhi, id_da, 0);
 								tc_commit(db_full);
+#endif
 #pragma unroll
 								for (int kk = 0; kk < 8; ++kk)
-									mma_ss_lh(tmem + kColDW5, al + kk * 128, dl + kk * 128, dhi, id_dw5t, acc | (kk > 0));
+									mma_ss_lh(dw_acc, al + kk * 128, dl + kk * 128, dhi, id_dw5t, acc | (kk > 0));
 							} else {
 								if (l > 0) {
+#if NRC_TRAIN_TS
+#pragma unroll
+									for (int kk = 0; kk < 4; ++kk)
+										mma_ts_lh(db_issue, ab_issue + kk * 8, wl + kk * 128, dhi, id_da, kk > 0);
+									tc_commit(db_full);
+									mbar_wait(ds_ready, ds_ph); // delta_l has reached shared memory too
+									ds_ph ^= 1;
+									tc_fence_after();
+#else
 #pragma unroll
 									for (int kk = 0; kk < 4; ++kk)
 										mma_ss_lh(db_issue, dl + kk * 2, wl + kk * 128, dhi, id_da, kk > 0);
 									tc_commit(db_full);
+#endif
 								}
 #pragma unroll
 								for (int kk = 0; kk < 8; ++kk)
-									mma_ss_lh(tmem + 64 * l, dl + kk * 128, al + kk * 128, dhi, id_dw64, acc | (kk > 0));
+									mma_ss_lh(dw_acc, dl + kk * 128, al + kk * 128, dhi, id_dw64, acc | (kk > 0));
 								if (l == 0 && !has_f) // the CTA's last tile of this batch: every dW accumulator is final
 									tc_commit(tile_done);
 								// (only where the wait below follows: every completed phase of dw1_done is consumed, so the
@@ -504,10 +655,10 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			// in the time the epilogue warps would spend waiting for the next accumulator.
 			auto stage_dw = [&](int l, float *stage) {
 				uint32_t v[32];
-				tmem_ld_x32(tmem_addr(tmem, q * 32, 64 * l + 32 * h), v);
+				tmem_ld_x32(tmem_addr(tmem, q * 32, dw_col(l) + 32 * h), v);
 				tc_wait_ld();
-				if (lane < 16) {
-					const uint32_t r = q * 16 + lane;
+				if ((lane & 16u) == dw_lane(l)) { // the 16 lanes of this quarter that hold dW_l's rows 16q .. 16q+15
+					const uint32_t r = q * 16 + (lane & 15u);
 					float4 *dst = (float4 *)(stage + r * 64);
 #pragma unroll
 					for (int i = 0; i < 8; ++i)
@@ -566,9 +717,19 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 #pragma unroll
 							for (int i = 0; i < 16; ++i)
 								o[i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+#if NRC_TRAIN_TS
+							tmem_st_x16(af_mine, o); // next layer's A operand: the forward chain only waits for this
+							arrive_tmem(af_ready);
+							NRC_GTRACE(0x20 + k);
+							// the shared-memory copy (dW_{k+1}'s operand and the ReLU mask of the backward pass) is off the chain: its first
+							// reader is issued after later arrivals of this warp, which order these stores and their proxy fence
+							store_half_row(pool_sm + fw[k + 1] * 16384, o);
+							fence_proxy_async_smem();
+#else
 							store_half_row(pool_sm + fw[k + 1] * 16384, o);
 							NRC_GTRACE(0x20 + k);
 							arrive_ready(af_ready);
+#endif
 						} else { // output layer + loss gradient (NN_nv.glsl:148-196) -> delta_5
 							if (h == 0) {
 								uint32_t yv[4];
@@ -598,11 +759,18 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 									yo[0] = y[0], yo[1] = y[1], yo[2] = y[2];
 								}
 								uint8_t *rr = delta_sm + row * 128; // delta_5 (buffer 0): 16 fp16 = logical chunks 0 and 1 of the row
+#if NRC_TRAIN_TS
+								const uint32_t d5[8] = {cvt_pack_f16x2(g[0], g[1]), cvt_pack_f16x2(g[2], 0.0f), 0u, 0u, 0u, 0u, 0u, 0u};
+								tmem_st_x8(tmem_addr(tmem, q * 32, kColAB), d5); // K = 16: the backward stream's first A operand
+#endif
 								*(uint4 *)(rr + ((0 ^ (row & 7)) << 4)) = make_uint4(cvt_pack_f16x2(g[0], g[1]), cvt_pack_f16x2(g[2], 0.0f), 0u, 0u);
 								*(uint4 *)(rr + ((1 ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
 							}
 							NRC_GTRACE(0x25);
 							arrive_ready(d5_ready); // delta_5 feeds backward layer 5 (step 0 of the next round)
+#if NRC_TRAIN_TS
+							arrive_ready(ds_ready); // (both copies are complete here: the loss epilogue is not on a per-layer chain)
+#endif
 							if (IN_MODE != NRC_IN_ENCODED && r + 1 < my_tiles) {
 								// a_0 of tile r + 1 -> the buffer of a_1 of tile r - 1 (bw[1]): its last reader (dW_1, step 4) was issued
 								// before this step's forward MMAs, whose commit has just been observed
@@ -634,17 +802,31 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							const __half2 dh = *(const __half2 *)&d2, ah = *(const __half2 *)&a[i];
 							o[i] = d2 & __hgt2_mask(ah, __float2half2_rn(0.0f)) & __heq2_mask(dh, dh);
 						}
+#if NRC_TRAIN_TS
+						if (l >= 2) { // delta_{l-1} feeds dA_{l-1} from tensor memory; the shared-memory copy (dW_{l-1}) follows off the chain
+							tmem_st_x16(ab_mine, o);
+							arrive_tmem(ab_ready);
+							NRC_GTRACE(0x40 + l);
+							store_half_row(delta_sm + ((6 - l) & 1) * 16384, o);
+							arrive_ready(ds_ready);
+						} else { // delta_0 only feeds dW_0
+							store_half_row(delta_sm + ((6 - l) & 1) * 16384, o);
+							NRC_GTRACE(0x40 + l);
+							arrive_ready(ab_ready);
+						}
+#else
 						store_half_row(delta_sm + ((6 - l) & 1) * 16384, o);
 						NRC_GTRACE(0x40 + l);
 						arrive_ready(ab_ready);
+#endif
 						if (last_round && l <= 4) { // dW_{l+1} is final (its MMAs precede this step's commits): drain it now
 							if (l == 4) {
 								if (h == 0) {
 									uint32_t v5[4];
-									tmem_ld_x4(tmem_addr(tmem, q * 32, kColDW5), v5); // dW_5^T: lane <-> in, column <-> out
+									tmem_ld_x4(tmem_addr(tmem, q * 32, dw_col(5)), v5); // dW_5^T: lane <-> in, column <-> out
 									tc_wait_ld();
-									if (lane < 16) {
-										float *dst = my_partial + 5 * 4096 + q * 16 + lane;
+									if ((lane & 16u) == dw_lane(5)) {
+										float *dst = my_partial + 5 * 4096 + q * 16 + (lane & 15u);
 										dst[0] = __uint_as_float(v5[0]), dst[64] = __uint_as_float(v5[1]), dst[128] = __uint_as_float(v5[2]);
 									}
 								}
@@ -715,7 +897,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		if (blockIdx.x == 0 && threadIdx.x == 0) { // (every CTA has passed this launch's first barrier: the old values are read)
 			if (b + 1 == tp.num_batches)
 				tp.grid_bar[1] = bar_target; // the launch's last barrier: publish the counter's final value as the next base
-			if (b == 0 && tp.comm.world > 1)
+			if (MULTI && b == 0 && tp.comm.world > 1)
 				*tp.comm.epoch_word = epoch_base - 1u + tp.num_batches;
 		}
 		{
@@ -737,7 +919,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 				old.t = os->t, old.beta1_t = os->beta1_t, old.beta2_t = os->beta2_t, old.alpha_t = os->alpha_t, old.alpha_t_1 = os->alpha_t_1;
 				st = advance_state(old);
 			}
-			const uint32_t world = tp.comm.world, me = tp.comm.rank, epoch = epoch_base + b, parity = epoch & 1u;
+			const uint32_t world = MULTI ? tp.comm.world : 1u, epoch = epoch_base + b;
 			// The 20 736 floats are cut in blocks of 64; CTA c owns blocks c, c + grid, ... and handles up to three of them
 			// per round. Per block: 16 threads x float4 cover the 64 floats of one partial, 16 groups of them take the
 			// partials g, g + 16, g + 32, ... (all loads in flight at once), and the 16 group sums are combined by a
@@ -806,71 +988,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 				}
 				float total_count = count;
 				bool cta_timed_out = false;
-				if (world > 1) {
-					// ---- all-reduce over NVLink, fused: push {value, epoch} words into every peer's inbox (one multicast store
-					// through the switch, or one store per peer), spin on the peers' words in my own inbox, add in rank order
-					// (identical operands in identical order on every rank)
-					const size_t dslot = (size_t)parity * NRC_MAX_RANKS * NRC_GRAD_STRIDE, cslot = kCommDataWords + (size_t)parity * NRC_MAX_RANKS;
-					const uint64_t tag = (uint64_t)epoch << 32;
-					bool timed_out = false;
-					if (mine_blk) {
-						const size_t at = dslot + (size_t)me * NRC_GRAD_STRIDE + my_i;
-						if (tp.comm.multicast) {
-							st_multicast(tp.comm.multicast + at, tag | __float_as_uint(sum));
-						} else {
-							for (uint32_t r = 0; r < world; ++r)
-								if (r != me)
-									st_peer(tp.comm.inbox[r] + at, tag | __float_as_uint(sum));
-						}
-					}
-					if (!have_peer_counts && threadIdx.x >= 192 && threadIdx.x < 192 + NRC_MAX_RANKS) { // one thread per peer: the record counts
-						const uint32_t r = threadIdx.x - 192;
-						if (blockIdx.x == 0) { // this rank's count: one word per source, published once per batch by CTA 0
-							if (tp.comm.multicast) {
-								if (r == me)
-									st_multicast(tp.comm.multicast + cslot + me, tag | __float_as_uint(count));
-							} else if (r < world && r != me) {
-								st_peer(tp.comm.inbox[r] + cslot + me, tag | __float_as_uint(count));
-							}
-						}
-						peer_counts[r] = r < world && r != me ? wait_peer(tp.comm.inbox[me] + cslot + r, epoch, tp.comm, timed_out) : 0u;
-					}
-					if (mine_blk) {
-						// all peers' words are requested at once and polled together (one L2 round trip when they have arrived, instead
-						// of one per peer: 7 dependent round trips were 2.5 us of every 8-GPU exchange), then added in rank order
-						const uint64_t *src = tp.comm.inbox[me] + dslot + my_i;
-						uint32_t val[NRC_MAX_RANKS];
-						uint32_t pending = ((1u << world) - 1u) & ~(1u << me);
-						for (uint32_t spins = 0; pending && !timed_out; ++spins) {
-							uint64_t got[NRC_MAX_RANKS];
-#pragma unroll
-							for (uint32_t r = 0; r < NRC_MAX_RANKS; ++r)
-								if (pending >> r & 1u)
-									asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(got[r]) : "l"(src + (size_t)r * NRC_GRAD_STRIDE) : "memory");
-#pragma unroll
-							for (uint32_t r = 0; r < NRC_MAX_RANKS; ++r)
-								if ((pending >> r & 1u) && (uint32_t)(got[r] >> 32) == epoch)
-									val[r] = (uint32_t)got[r], pending &= ~(1u << r);
-							if (pending && spins > tp.comm.spin_limit) {
-								timed_out = true;
-								atomicExch(tp.comm.error_word, 1u);
-							}
-							if (pending && spins > 16)
-								__nanosleep(32);
-						}
-						float tot = 0.0f;
-#pragma unroll
-						for (uint32_t r = 0; r < NRC_MAX_RANKS; ++r)
-							if (r < world)
-								tot += r == me ? sum : (pending >> r & 1u) ? 0.0f : __uint_as_float(val[r]);
-						sum = tot;
-					}
-					cta_timed_out = __syncthreads_or(timed_out ? 1 : 0) != 0;
-					have_peer_counts = true;
-					total_count = 0.0f;
-					for (uint32_t r = 0; r < world; ++r)
-						total_count += r == me ? count : __uint_as_float(peer_counts[r]); // integers < 2^24: exact
-				}
+				if (MULTI && world > 1)
+					cta_timed_out = exchange_with_peers(tp.comm, epoch, mine_blk, my_i, count, have_peer_counts, peer_counts, sum, total_count);
 				if (mine) {
 					const bool do_adam = adam_mode != 0 && total_count > 0.0f && !cta_timed_out; // nrc_optimize.comp:33-34 / nrc_train_prepare.comp:22
 					any_adam = any_adam || do_adam;
@@ -919,9 +1038,9 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 
 uint32_t gradient_max_partials(int sms) { return (uint32_t)sms; }
 
-template <int IN_MODE>
+template <int IN_MODE, bool MULTI>
 static cudaError_t launch_train_t(const TrainParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, uint32_t grid, cudaStream_t stream) {
-	auto kern = nrc_train_kernel<IN_MODE>;
+	auto kern = nrc_train_kernel<IN_MODE, MULTI>;
 	static std::atomic<uint64_t> configured{0}; // function attributes are per device: one bit per device ordinal
 	int dev = 0;
 	if (cudaError_t e = cudaGetDevice(&dev); e != cudaSuccess)
@@ -953,15 +1072,16 @@ cudaError_t launch_train(const TrainParams &p, const CUtensorMap &tm_w, const CU
 		*grid_out = grid;
 	TrainParams q = p;
 	q.pool_tiles = ntiles > grid ? 8u : 6u; // two tiles in flight only where a CTA has more than one
+	const bool multi = p.comm.world > 1;
 	switch (p.batch[0].in_mode) {
 	case NRC_IN_ENCODED:
-		return launch_train_t<NRC_IN_ENCODED>(q, tm_w, tm_in, grid, stream);
+		return multi ? launch_train_t<NRC_IN_ENCODED, true>(q, tm_w, tm_in, grid, stream) : launch_train_t<NRC_IN_ENCODED, false>(q, tm_w, tm_in, grid, stream);
 	case NRC_IN_UNPACKED:
-		return launch_train_t<NRC_IN_UNPACKED>(q, tm_w, tm_in, grid, stream);
+		return multi ? launch_train_t<NRC_IN_UNPACKED, true>(q, tm_w, tm_in, grid, stream) : launch_train_t<NRC_IN_UNPACKED, false>(q, tm_w, tm_in, grid, stream);
 	case NRC_IN_IMAGE_RANDOM:
-		return launch_train_t<NRC_IN_IMAGE_RANDOM>(q, tm_w, tm_in, grid, stream);
+		return launch_train_t<NRC_IN_IMAGE_RANDOM, false>(q, tm_w, tm_in, grid, stream); // (the learn-an-image harness is single-GPU)
 	case NRC_IN_PACKED:
-		return launch_train_t<NRC_IN_PACKED>(q, tm_w, tm_in, grid, stream);
+		return multi ? launch_train_t<NRC_IN_PACKED, true>(q, tm_w, tm_in, grid, stream) : launch_train_t<NRC_IN_PACKED, false>(q, tm_w, tm_in, grid, stream);
 	}
 	return cudaErrorInvalidValue;
 }
