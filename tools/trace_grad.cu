@@ -61,7 +61,16 @@ int main(int argc, char **argv) {
 	}
 	static uint2 tr[NRC_GTRACE_CAP]; unsigned int cnt;
 	cudaMemcpyFromSymbol(tr, g_nrc_gtrace, sizeof(tr)); cudaMemcpyFromSymbol(&cnt, g_nrc_gtrace_n, sizeof(cnt));
-	for (unsigned i = 0; i < cnt; ++i)
-		printf("ev=0x%02x t=%u (+%u)\n", tr[i].x, tr[i].y - tr[0].y, i ? tr[i].y - tr[i - 1].y : 0);
+	static uint2 it[NRC_GTRACE_CAP]; unsigned int icnt;
+	cudaMemcpyFromSymbol(it, g_nrc_itrace, sizeof(it)); cudaMemcpyFromSymbol(&icnt, g_nrc_itrace_n, sizeof(icnt));
+	// merged by time stamp: epilogue thread (tags < 0x100) and issuing thread (0x16k F wait done, 0x17k F issued, 0x18l B wait done,
+	// 0x19l dA issued, 0x1Al delta in smem, 0x1Bl dW issued)
+	unsigned a = 0, b = 0; uint32_t prev = tr[0].y;
+	while (a < cnt || b < icnt) {
+		const bool take_a = b >= icnt || (a < cnt && (int32_t)(tr[a].y - it[b].y) <= 0);
+		const uint2 e = take_a ? tr[a++] : it[b++];
+		printf("%s ev=0x%03x t=%u (+%u)\n", take_a ? "epi  " : "issue", e.x, e.y - tr[0].y, e.y - prev);
+		prev = e.y;
+	}
 	return 0;
 }

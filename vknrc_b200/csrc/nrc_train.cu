@@ -41,17 +41,27 @@ __device__ unsigned int g_nrc_gtrace_n;
 		if (blockIdx.x == 0 && threadIdx.x == 0 && gtrace_n < NRC_GTRACE_CAP)                                          \
 			gtrace[gtrace_n++] = make_uint2((uint32_t)(tag), (uint32_t)clock64());                                     \
 	} while (0)
+// the issuing thread's own timeline (tags 0x100 + ...): merged with the epilogue thread's by time stamp when dumped
+__device__ uint2 g_nrc_itrace[NRC_GTRACE_CAP];
+__device__ unsigned int g_nrc_itrace_n;
+#define NRC_ITRACE(tag)                                                                                                \
+	do {                                                                                                               \
+		if (blockIdx.x == 0 && itrace_n < NRC_GTRACE_CAP)                                                              \
+			itrace[itrace_n++] = make_uint2((uint32_t)(tag), (uint32_t)clock64());                                     \
+	} while (0)
 #elif defined(NRC_GTRACE_FENCE) // experiment: the trace points as pure compiler scheduling fences
 #define NRC_GTRACE(tag) asm volatile("" ::: "memory")
+#define NRC_ITRACE(tag)
 #else
 #define NRC_GTRACE(tag)
+#define NRC_ITRACE(tag)
 #endif
 
 #ifndef NRC_COMM_POLL_PARALLEL
 #define NRC_COMM_POLL_PARALLEL 0
 #endif
 #ifndef NRC_TRAIN_TS
-#define NRC_TRAIN_TS 0
+#define NRC_TRAIN_TS 1 // 0: the round-1 form (all operands from shared memory, dW accumulators side by side)
 #endif
 
 namespace nrc {
@@ -310,7 +320,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	uint32_t *tmem_slot = (uint32_t *)(bars + 11);
 #ifdef NRC_TRACE
 	__shared__ uint2 gtrace[NRC_GTRACE_CAP];
-	uint32_t gtrace_n = 0;
+	__shared__ uint2 itrace[NRC_GTRACE_CAP];
+	uint32_t gtrace_n = 0, itrace_n = 0;
 #endif
 	NRC_GTRACE(1);
 
@@ -559,6 +570,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 								af_ph ^= 1;
 							}
 							tc_fence_after();
+							NRC_ITRACE(0x160 + k);
 							const uint32_t a_d = pool_desc + fw[k] * (16384 >> 4), b_d = w_desc + (uint32_t)(k * (8192 >> 4));
 #if NRC_TRAIN_TS
 							if (!(IN_MODE == NRC_IN_ENCODED && k == 0)) { // a_k from tensor memory (pre-encoded a_0 arrives in shared memory by TMA)
@@ -573,6 +585,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 									mma_ss_lh(df_issue, a_d + kk * 2, b_d + kk * 2, dhi, k < 5 ? id_fwd64 : id_fwd16, kk > 0);
 							}
 							tc_commit(df_full);
+							NRC_ITRACE(0x170 + k);
 						}
 						if (has_b) { // ---- backward layer l of tile r - 1: dA first (critical path), then dW_l
 							if (l < 5) {
@@ -580,6 +593,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 								ab_ph ^= 1;
 							}
 							tc_fence_after();
+							NRC_ITRACE(0x180 + l);
 							const uint32_t dl = del_desc + (uint32_t)(((5 - l) & 1) * (16384 >> 4));
 							const uint32_t al = pool_desc + bw[l] * (16384 >> 4), wl = w_desc + (uint32_t)(l * (8192 >> 4));
 							const uint32_t acc = (r > 1) ? 1u : 0u; // dW accumulates from the CTA's second tile on
@@ -605,9 +619,11 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 									for (int kk = 0; kk < 4; ++kk)
 										mma_ts_lh(db_issue, ab_issue + kk * 8, wl + kk * 128, dhi, id_da, kk > 0);
 									tc_commit(db_full);
+									NRC_ITRACE(0x190 + l);
 									mbar_wait(ds_ready, ds_ph); // delta_l has reached shared memory too
 									ds_ph ^= 1;
 									tc_fence_after();
+									NRC_ITRACE(0x1A0 + l);
 #else
 #pragma unroll
 									for (int kk = 0; kk < 4; ++kk)
@@ -618,6 +634,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 #pragma unroll
 								for (int kk = 0; kk < 8; ++kk)
 									mma_ss_lh(dw_acc, dl + kk * 128, al + kk * 128, dhi, id_dw64, acc | (kk > 0));
+								NRC_ITRACE(0x1B0 + l);
 								if (l == 0 && !has_f) // the CTA's last tile of this batch: every dW accumulator is final
 									tc_commit(tile_done);
 								// (only where the wait below follows: every completed phase of dw1_done is consumed, so the
@@ -1028,6 +1045,11 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		for (uint32_t i = 0; i < gtrace_n; ++i)
 			g_nrc_gtrace[i] = gtrace[i];
 		g_nrc_gtrace_n = gtrace_n;
+	}
+	if (blockIdx.x == 0 && warp == kIssueWarp && itrace_n) { // (only the elected issuing thread has logged anything)
+		for (uint32_t i = 0; i < itrace_n; ++i)
+			g_nrc_itrace[i] = itrace[i];
+		g_nrc_itrace_n = itrace_n;
 	}
 #endif
 	tc_fence_before();
