@@ -43,11 +43,23 @@ def make_scene_arrays(seed: int, n_prims: int = 500, n_instances: int = 3, n_mat
             "materials": mats, "material_ids": material_ids, "transforms": transforms, "textures": textures}
 
 
-def random_packed_inputs(seed: int, n: int, n_prims: int, n_instances: int) -> np.ndarray:
-    """[n,4] uint32 PackedNRCInput (NRCRecord.glsl:6-10): primitive, flip bit | instance, barycentric y,z, scattered dir."""
+def prim_instance_ids(n_prims: int, n_instances: int) -> np.ndarray:
+    """The instance every primitive belongs to: contiguous primitive ranges, as the reference's scene loader produces (one OBJ
+    split into instances, each primitive in exactly one; src/Scene.cpp) - the path tracer's records always pair a primitive with
+    its own instance."""
+    return (np.arange(n_prims, dtype=np.uint64) * n_instances // max(1, n_prims)).astype(np.uint32)
+
+
+def random_packed_inputs(seed: int, n: int, n_prims: int, n_instances: int, any_instance: bool = False) -> np.ndarray:
+    """[n,4] uint32 PackedNRCInput (NRCRecord.glsl:6-10): primitive, flip bit | instance, barycentric y,z, scattered dir.
+    The instance is the primitive's own (prim_instance_ids) unless `any_instance` (arbitrary pairs: legal for the shader, never
+    produced by the path tracer; exercises the per-record fallback of the normal table)."""
     rng = np.random.default_rng(seed)
     prim = rng.integers(0, n_prims, n).astype(np.uint32)
-    inst = rng.integers(0, n_instances, n).astype(np.uint32) | (rng.integers(0, 2, n).astype(np.uint32) << 31)
+    inst = rng.integers(0, n_instances, n).astype(np.uint32)
+    if not any_instance:
+        inst = prim_instance_ids(n_prims, n_instances)[prim]
+    inst = inst | (rng.integers(0, 2, n).astype(np.uint32) << 31)
     b = rng.dirichlet((1, 1, 1), n)
     bary = (np.round(b[:, 1] * 65535).astype(np.uint32) & 0xFFFF) | (np.round(b[:, 2] * 65535).astype(np.uint32) << 16)
     sd = rng.integers(0, 65536, (n, 2)).astype(np.uint32)
