@@ -530,9 +530,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			fw[0] = n0, fw[1] = n1, fw[2] = n2, fw[3] = n3, fw[4] = n4, fw[5] = n5;
 		};
 
-		if (my_tiles == 0) { // nothing to do: contribute an all-zero partial so the reduction stays shape-stable
-			for (uint32_t i = threadIdx.x; i < NRC_GRAD_STRIDE; i += blockDim.x)
-				my_partial[i] = 0.0f;
+		if (my_tiles == 0) {
+			// nothing to do in the gradient phase: the reduction below only reads the partials of the CTAs that had a tile
 		} else if (warp == kIssueWarp) {
 			// ================================================================================== issue warp
 			if (elect_one()) {
@@ -918,7 +917,9 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 				*tp.comm.epoch_word = epoch_base - 1u + tp.num_batches;
 		}
 		{
-			const uint32_t num_partials = gridDim.x;
+			// (every CTA with a tile in this batch wrote one partial: CTAs 0 .. min(grid, #tiles) - 1)
+			const uint64_t batch_tiles = (n + NRC_TILE - 1) / NRC_TILE;
+			const uint32_t num_partials = batch_tiles < gridDim.x ? (uint32_t)batch_tiles : gridDim.x;
 			// the batch's record count: integers < 2^24, so any summation order is exact (the load is issued here, its
 			// reduction happens below, under the latency of the partial loads)
 			float cnt_part = threadIdx.x < num_partials ? ld_cg(p.partials + (size_t)threadIdx.x * NRC_GRAD_STRIDE + NRC_GRAD_COUNT_SLOT) : 0.0f;
@@ -1084,12 +1085,18 @@ static cudaError_t launch_train_t(const TrainParams &p, const CUtensorMap &tm_w,
 }
 
 cudaError_t launch_train(const TrainParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream, uint32_t *grid_out) {
-	uint64_t ntiles = 1; // an empty batch still runs one CTA: it emits an all-zero partial and runs the reduction
+	uint64_t ntiles = 1;
 	for (uint32_t b = 0; b < p.num_batches; ++b) {
 		const uint64_t t = (p.batch[b].n + NRC_TILE - 1) / NRC_TILE;
 		ntiles = t > ntiles ? t : ntiles;
 	}
-	const uint32_t grid = (uint32_t)(ntiles < (uint64_t)sms ? ntiles : (uint64_t)sms);
+	// One CTA per tile up to the number of SMs - but never fewer than 108: the reduction / exchange / optimizer phase handles
+	// the 324 blocks of the gradient three per CTA and round, and with a small batch (a shard of 2048 records is 16 tiles) a
+	// 16-CTA grid would walk seven rounds one after the other, every one with its own wait for the peers' words (8 GPUs, 4 x
+	// 16 384 records sharded: 208 us per frame). CTAs without a tile skip the gradient phase and write no partial.
+	const uint64_t min_grid = 108 < sms ? 108 : sms;
+	const uint64_t want = ntiles > min_grid ? ntiles : min_grid;
+	const uint32_t grid = (uint32_t)(want < (uint64_t)sms ? want : (uint64_t)sms);
 	if (grid_out)
 		*grid_out = grid;
 	TrainParams q = p;
