@@ -4,13 +4,15 @@
  * TEST INFRASTRUCTURE ONLY. Nothing in vknrc_b200/ (the product) may import, link or execute this file; only
  * tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs use it, as the checker.
  *
- * Parity status: the reference ships NO golden vectors, fixtures or thresholds, so this oracle is
- * pinned the only way available: (1) its forward pass is checked against the reference's own CPU `Evaluate`
- * (test/main.cpp:11-27) compiled unmodified into oracle/_ref/ (tests/test_oracle.py), (2) its backward pass is
- * checked by finite differences and against the one meaningful part of the reference's CPU `Train` (layer-5 dW,
- * SURVEY Q13), (3) tests/golden/ holds vectors generated in this container from (1) by tools/make_golden.py.
- * The GLSL shaders themselves cannot be executed here (no Vulkan), so GPU-side parity stays "pinned by the
- * reference's CPU path + restatement", not by reference-GPU outputs.
+ * Parity status: the reference ships NO golden vectors, fixtures or thresholds; this oracle is pinned by
+ * reference code executed here: (1) its forward pass against the reference's own CPU `Evaluate` (test/main.cpp:11-27)
+ * compiled unmodified into oracle/_ref/ (tests/test_oracle.py, tests/golden/nrc_golden_v1.npz); (2) every other function -
+ * encoding, scene gather, dst codec, loss gradients, backward pass, dW reduction, prepare + optimizer, scatter, the
+ * learn-an-image kernels - against the reference's own GLSL SHADERS compiled as C++ and run on the CPU (oracle/glsl ->
+ * oracle/_ref_glsl, tests/golden/nrc_golden_v2.npz, tests/test_ref_glsl.py): bit-exact for encoding, forward in shader
+ * precision, optimizer, dst codec; to the order of the shader's fp32 atomics for the gradients. What stays an assumption
+ * is how the GPU's cooperative-matrix MMA and texture unit round internally (E1, E2 in oracle/glsl/glsl_shim.hpp): the
+ * GLSL cannot be executed on a GPU here (no Vulkan loader / ICD).
  *
  * Every function cites the reference lines it follows (paths relative to /root/reference).
  * Build: see oracle/Makefile (gcc -O2 -mf16c -ffp-contract=off: no FMA contraction, so fp32 steps round

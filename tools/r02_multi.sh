@@ -2,7 +2,7 @@
 # N-GPU round trip: GPU tests (incl. the multi-GPU worker tests), bench at N, reference arm placeholder, sweep at N, fixed-cost probe
 N=${1:-8}
 mkdir -p gpurun_out
-python -m pytest tests/test_multi_gpu.py -x -q -m gpu 2>&1 | tail -3
+# (tests/test_multi_gpu.py runs the same worker as the last line)
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29530 bench.py --gpus $N --steps 100 --warmup 5 > gpurun_out/bench_${N}gpu.json 2> gpurun_out/bench_${N}gpu.err; echo "bench rc=$?"; grep -v "^\[W\|^$\|\*\*\*\|OMP_NUM" gpurun_out/bench_${N}gpu.err | tail -5
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29531 tools/sweep.py > gpurun_out/sweep_${N}gpu.txt 2>&1; grep -v "^\[W\|^$\|\*\*\*\|OMP_NUM" gpurun_out/sweep_${N}gpu.txt | tail -18
 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29532 tests/mgpu_worker.py 2>&1 | grep MGPU_RESULT > gpurun_out/mgpu_${N}gpu.txt; cat gpurun_out/mgpu_${N}gpu.txt
