@@ -5,6 +5,7 @@
 // 0x56 Adam done, 0x57 CTA barrier), 10 exit).
 #include "../vknrc_b200/csrc/nrc_train.cu"
 #include <cstdio>
+#include <climits>
 #include <vector>
 typedef CUresult (*PFN)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
                         const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -32,6 +33,17 @@ int main(int argc, char **argv) {
 	}
 	CUtensorMap tw; mk(&tw, w, 323, 64);
 	const int nb = argc > 2 ? atoi(argv[2]) : 1; // batches per launch (frame = 4)
+	const bool encoded = argc > 3 && atoi(argv[3]) == 0; // argv[3]: 1 = 14-float records (default), 0 = pre-encoded inputs
+	__half *enc = nullptr, *tgt16 = nullptr; CUtensorMap tin = tw;
+	if (encoded) {
+		cudaMalloc(&enc, n * 128); cudaMalloc(&tgt16, n * 6);
+		std::vector<__half> he(n * 64), ht(n * 3);
+		uint32_t x = 777u; auto rnd = [&]() { x = x * 1664525u + 1013904223u; return (float)(x >> 8) * (1.0f / 16777216.0f); };
+		for (auto &v : he) v = __float2half(rnd());
+		for (auto &v : ht) v = __float2half(rnd());
+		cudaMemcpy(enc, he.data(), he.size() * 2, cudaMemcpyHostToDevice); cudaMemcpy(tgt16, ht.data(), ht.size() * 2, cudaMemcpyHostToDevice);
+		mk(&tin, enc, n, 128);
+	}
 	NrcOptimizerEntry *entries; NrcOptimizerState *ost; uint32_t *sync; float *grads; __half *uw;
 	cudaMalloc(&entries, 20672 * 16); cudaMalloc(&ost, 20); cudaMalloc(&sync, 32); cudaMalloc(&grads, NRC_GRAD_STRIDE * 4); cudaMalloc(&uw, 6 * 8192);
 	cudaMemset(sync, 0, 32);
@@ -47,6 +59,7 @@ int main(int argc, char **argv) {
 		nrc::GradParams &p = tp.batch[b];
 		p.n = n; p.in_mode = nrc::NRC_IN_UNPACKED; p.loss_kind = nrc::NRC_LOSS_RELATIVE_L2_LUMINANCE; p.loss_scale = 1.0f;
 		p.in = rec; p.in_stride_bytes = 56; p.target = tgt; p.target_stride_bytes = 12; p.partials = partials;
+		if (encoded) { p.in_mode = nrc::NRC_IN_ENCODED; p.target = tgt16; p.target_stride_bytes = 6; p.target_is_f16 = 1; }
 		tp.adam_mode[b] = b == nb - 1 ? 2 : 1;
 	}
 	tp.num_batches = nb; tp.gradients = grads; tp.limit = NRC_GRAD_STRIDE; tp.batch_cap = (uint32_t)n; tp.grid_bar = sync + 2;
@@ -54,7 +67,7 @@ int main(int argc, char **argv) {
 	cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
 	for (int it = 0; it < 4; ++it) {
 		cudaEventRecord(e0);
-		cudaError_t le = nrc::launch_train(tp, tw, tw, 148, 0);
+		cudaError_t le = nrc::launch_train(tp, tw, tin, 148, 0);
 		cudaEventRecord(e1);
 		cudaError_t e = cudaDeviceSynchronize();
 		float ms; cudaEventElapsedTime(&ms, e0, e1); printf("train kernel (%d batch%s of %llu) %.1f us (%s / %s)\n", nb, nb > 1 ? "es" : "", (unsigned long long)n, ms * 1e3, cudaGetErrorString(le), cudaGetErrorString(e));
@@ -63,13 +76,19 @@ int main(int argc, char **argv) {
 	cudaMemcpyFromSymbol(tr, g_nrc_gtrace, sizeof(tr)); cudaMemcpyFromSymbol(&cnt, g_nrc_gtrace_n, sizeof(cnt));
 	static uint2 it[NRC_GTRACE_CAP]; unsigned int icnt;
 	cudaMemcpyFromSymbol(it, g_nrc_itrace, sizeof(it)); cudaMemcpyFromSymbol(&icnt, g_nrc_itrace_n, sizeof(icnt));
-	// merged by time stamp: epilogue thread (tags < 0x100) and issuing thread (0x16k F wait done, 0x17k F issued, 0x18l B wait done,
-	// 0x19l dA issued, 0x1Al delta in smem, 0x1Bl dW issued)
-	unsigned a = 0, b = 0; uint32_t prev = tr[0].y;
-	while (a < cnt || b < icnt) {
-		const bool take_a = b >= icnt || (a < cnt && (int32_t)(tr[a].y - it[b].y) <= 0);
-		const uint2 e = take_a ? tr[a++] : it[b++];
-		printf("%s ev=0x%03x t=%u (+%u)\n", take_a ? "epi  " : "issue", e.x, e.y - tr[0].y, e.y - prev);
+	static uint2 pt[NRC_GTRACE_CAP]; unsigned int pcnt;
+	cudaMemcpyFromSymbol(pt, g_nrc_ptrace, sizeof(pt)); cudaMemcpyFromSymbol(&pcnt, g_nrc_ptrace_n, sizeof(pcnt));
+	// merged by time stamp: epilogue thread (tags < 0x100), issuing thread (0x16k F wait done, 0x17k F issued, 0x18l B wait done,
+	// 0x19l dA issued, 0x1Al delta in smem, 0x1Bl dW issued) and the first producer thread (0x200+t unit of tile t started, 0x210+t
+	// encoded, 0x220+t stored and arrived)
+	unsigned a = 0, b = 0, c = 0; uint32_t prev = tr[0].y;
+	const unsigned lim = argc > 4 ? atoi(argv[4]) : 400;
+	while ((a < cnt || b < icnt || c < pcnt) && a + b + c < lim) {
+		const int32_t ta = a < cnt ? (int32_t)(tr[a].y - tr[0].y) : INT32_MAX, tb = b < icnt ? (int32_t)(it[b].y - tr[0].y) : INT32_MAX,
+		              tc = c < pcnt ? (int32_t)(pt[c].y - tr[0].y) : INT32_MAX;
+		const int who = ta <= tb && ta <= tc ? 0 : (tb <= tc ? 1 : 2);
+		const uint2 e = who == 0 ? tr[a++] : who == 1 ? it[b++] : pt[c++];
+		printf("%s ev=0x%03x t=%u (+%u)\n", who == 0 ? "epi  " : who == 1 ? "issue" : "prod ", e.x, e.y - tr[0].y, e.y - prev);
 		prev = e.y;
 	}
 	return 0;

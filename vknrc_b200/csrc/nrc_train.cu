@@ -7,7 +7,8 @@
 //   src/rg/NRCRenderGraph.cpp:57-70).
 //
 // nrc_train_kernel, per CTA (one 128-record tile at a time; 8 epilogue warps = 4 TMEM lane quarters x 2 column
-// halves, plus one issue warp whose elected thread issues every TMA load and tcgen05.mma):
+// halves, one issue warp whose elected thread issues every TMA load and tcgen05.mma, and 3 producer warps that unpack +
+// encode the records of the tile after next into a spare activation buffer - a whole round ahead of the forward pass):
 //   every operand tile is an array of 128-byte rows (64 fp16) in shared memory with the 128-byte swizzle:
 //     W_l      [out][in]     used K-major  (forward B)   and MN-major (dA: B with K = out)
 //     a_l      [sample][in]  used K-major  (forward A)   and MN-major (dW: B with K = sample)
@@ -32,14 +33,15 @@
 using namespace sm100;
 
 #ifdef NRC_TRACE
-// development aid (tools/trace_grad.cu): thread 0 of CTA 0 logs (tag, clock) pairs; dumped when the kernel ends
-#define NRC_GTRACE_CAP 256
+// development aid (tools/trace_grad.cu): thread 0 of CTA 0 logs (tag, clock) pairs straight into global memory (fire-and-forget
+// stores; the kernel's shared memory is full)
+#define NRC_GTRACE_CAP 512
 __device__ uint2 g_nrc_gtrace[NRC_GTRACE_CAP];
 __device__ unsigned int g_nrc_gtrace_n;
 #define NRC_GTRACE(tag)                                                                                                \
 	do {                                                                                                               \
 		if (blockIdx.x == 0 && threadIdx.x == 0 && gtrace_n < NRC_GTRACE_CAP)                                          \
-			gtrace[gtrace_n++] = make_uint2((uint32_t)(tag), (uint32_t)clock64());                                     \
+			g_nrc_gtrace[gtrace_n++] = make_uint2((uint32_t)(tag), (uint32_t)clock64());                               \
 	} while (0)
 // the issuing thread's own timeline (tags 0x100 + ...): merged with the epilogue thread's by time stamp when dumped
 __device__ uint2 g_nrc_itrace[NRC_GTRACE_CAP];
@@ -47,14 +49,24 @@ __device__ unsigned int g_nrc_itrace_n;
 #define NRC_ITRACE(tag)                                                                                                \
 	do {                                                                                                               \
 		if (blockIdx.x == 0 && itrace_n < NRC_GTRACE_CAP)                                                              \
-			itrace[itrace_n++] = make_uint2((uint32_t)(tag), (uint32_t)clock64());                                     \
+			g_nrc_itrace[itrace_n++] = make_uint2((uint32_t)(tag), (uint32_t)clock64());                               \
+	} while (0)
+// one producer thread's timeline (tags 0x200 + ...)
+__device__ uint2 g_nrc_ptrace[NRC_GTRACE_CAP];
+__device__ unsigned int g_nrc_ptrace_n;
+#define NRC_PTRACE(tag)                                                                                                \
+	do {                                                                                                               \
+		if (blockIdx.x == 0 && threadIdx.x == kProducerWarp0 * 32 && ptrace_n < NRC_GTRACE_CAP)                        \
+			g_nrc_ptrace[ptrace_n++] = make_uint2((uint32_t)(tag), (uint32_t)clock64());                               \
 	} while (0)
 #elif defined(NRC_GTRACE_FENCE) // experiment: the trace points as pure compiler scheduling fences
 #define NRC_GTRACE(tag) asm volatile("" ::: "memory")
 #define NRC_ITRACE(tag)
+#define NRC_PTRACE(tag)
 #else
 #define NRC_GTRACE(tag)
 #define NRC_ITRACE(tag)
+#define NRC_PTRACE(tag)
 #endif
 
 #ifndef NRC_COMM_POLL_PARALLEL
@@ -68,11 +80,14 @@ namespace nrc {
 
 namespace {
 constexpr uint32_t kWOff = 0;                         // 6 x 8 KB weights
-constexpr uint32_t kPoolOff = NRC_LAYERS * 8192;      // P x 16 KB activation tiles (also fp32 staging of the partial): P = 8 when a CTA
-                                                      // runs several tiles (two in flight), 6 when every CTA has at most one - the smaller
-                                                      // footprint leaves the L1 32 KB more, which the latency-bound frame feels (-2 us)
-// then 2 x 16 KB deltas (ping-pong: delta_l lives in buffer (5 - l) & 1), then the barriers
+constexpr uint32_t kPoolOff = NRC_LAYERS * 8192;      // P x 16 KB activation tiles (also fp32 staging of the partial): P = 9 when a CTA
+                                                      // runs several tiles (two in flight + the input tile of the one after), 6 when every
+                                                      // CTA has at most one - the smaller footprint leaves the L1 more, which the
+                                                      // latency-bound frame feels (-2 us)
+// then 2 x 16 KB deltas (ping-pong: delta_l lives in buffer (5 - l) & 1; scratch of the reduction phase), then the barriers
+constexpr uint32_t kPoolMulti = 9, kPoolSingle = 6;
 constexpr uint32_t train_smem_bytes(uint32_t pool_tiles) { return kPoolOff + (pool_tiles + 2) * 16384 + 256 + 1024; }
+static_assert(train_smem_bytes(kPoolMulti) + 256 <= 232448, "dynamic + static shared memory of a CTA");
 #if NRC_TRAIN_TS
 // TMEM map (columns x lanes): the M=64 dW accumulators occupy 16 of every 32 lanes, so two of them share 64 columns - dW_l at
 // columns 64*(l/2), lane offset 16*(l%2) (dW_4 with dW_5^T) - 192 columns instead of 336. That leaves room for the fp16 A
@@ -89,9 +104,42 @@ __device__ __forceinline__ constexpr uint32_t dw_col(int l) { return l == 5 ? kC
 __device__ __forceinline__ constexpr uint32_t dw_lane(int) { return 0u; }
 #endif
 constexpr uint32_t kEpiWarps = 8, kEpiThreads = 256, kIssueWarp = 8;
-constexpr int kTrainThreads = 288;
+constexpr uint32_t kProducerWarp0 = 9, kProducerWarps = 3; // record input modes: raw record -> a_0, a tile ahead of the forward pass
+constexpr int kMainThreads = 288;                           // warps 0..8: every CTA-wide barrier of the batch loop (named barrier 2)
+constexpr int kTrainThreads = 384;
 constexpr uint32_t kReduceBlocks = NRC_GRAD_STRIDE / 64; // the reduction works on blocks of 64 consecutive floats
 static_assert(NRC_GRAD_STRIDE % 64 == 0, "the reduction works on 64-float blocks");
+// Activation tiles of a CTA that runs several tiles per batch live in a ring of nine 16 KB buffers. Round r carries the forward
+// pass of tile r (a_0..a_5 in fw[]) and the backward pass of tile r - 1 (bw[]): the forward tile holds a_0..a_{k+1} and the
+// backward tile a_0..a_l at step k (l = 5 - k), (k + 2) + (l + 1) = 8 buffers, and the ninth (nx) receives a_0 of tile r + 1
+// while the round runs. A buffer is handed over the moment its last reader is done:
+//   a_{k+1} of a tile takes the buffer of a_{6-k} of the tile before it (k >= 1; freed by dW_{6-k} one step earlier),
+//   a_1 takes the buffer of a_0 two tiles back (freed by dW_0 at the end of the previous round),
+//   the next spare buffer is the one of a_1 two tiles back (freed by dW_1, step 4 of the previous round).
+// The issuing thread, the epilogue warps and the producer warps each step their own copy; it restarts with every batch.
+struct TileRing {
+	uint32_t fw[6] = {0, 1, 2, 3, 4, 5}, bw[6] = {7, 6, 0, 0, 0, 0}, nx = 8;
+	__device__ __forceinline__ void rotate() {
+		const uint32_t n0 = nx, n1 = bw[0], n2 = fw[5], n3 = fw[4], n4 = fw[3], n5 = fw[2], spare = bw[1];
+#pragma unroll
+		for (int i = 0; i < 6; ++i)
+			bw[i] = fw[i];
+		fw[0] = n0, fw[1] = n1, fw[2] = n2, fw[3] = n3, fw[4] = n4, fw[5] = n5, nx = spare;
+	}
+};
+
+// CTA-wide barriers of the training kernel's batch loop: warps 0..8 only (named barrier 2). The producer warps run ahead of
+// the batch loop on their own schedule - they encode the next batch's first tile while these warps reduce the current
+// batch's gradient - and meet the others again at the kernel's final __syncthreads.
+__device__ __forceinline__ void main_sync() { asm volatile("bar.sync 2, %0;" ::"n"(kMainThreads) : "memory"); }
+__device__ __forceinline__ bool main_sync_or(bool pred) {
+	uint32_t r;
+	asm volatile("{\n\t.reg .pred p, q;\n\tsetp.ne.u32 p, %1, 0;\n\tbarrier.red.or.pred q, 2, %2, p;\n\tselp.u32 %0, 1, 0, q;\n\t}"
+	             : "=r"(r)
+	             : "r"((uint32_t)pred), "n"(kMainThreads)
+	             : "memory");
+	return r != 0;
+}
 } // namespace
 
 // bilinear RGBA8 fetch, clamp-to-edge, normalised coordinates (the sampler of mlp_learning_an_image/main.cpp:121-124)
@@ -144,8 +192,8 @@ __device__ __forceinline__ void adam_update(const AdamParams &a, uint32_t i, Nrc
 }
 // The last CTA to finish publishes the advanced state: every CTA has derived it from the old one before arriving, so
 // no CTA can observe a half-updated state and no extra launch is needed.
+// (the caller has put a CTA-wide barrier in front: every thread's entries / weights are written)
 __device__ __forceinline__ void publish_state_if_last(const AdamParams &a, const NrcOptimizerState &st) {
-	__syncthreads();
 	if (threadIdx.x == 0) {
 		__threadfence();
 		if (atomicAdd(a.done_counter, 1u) == gridDim.x - 1) {
@@ -174,7 +222,7 @@ __device__ __forceinline__ void publish_state_if_last(const AdamParams &a, const
 template <bool kProxyFence> __device__ __forceinline__ void grid_sync(uint32_t *counter, uint32_t &target) {
 	if (kProxyFence)
 		asm volatile("fence.proxy.async;" ::: "memory");
-	__syncthreads();
+	main_sync();
 	if (threadIdx.x == 0) {
 		target += gridDim.x;
 		__threadfence();
@@ -187,7 +235,7 @@ template <bool kProxyFence> __device__ __forceinline__ void grid_sync(uint32_t *
 			__nanosleep(NRC_GRID_SYNC_BACKOFF); // 148 pollers on one L2 line slow the arrivals down: 2440 -> 2320 cycles
 		}
 	}
-	__syncthreads();
+	main_sync();
 }
 
 __device__ __forceinline__ float ld_cg(const float *p) { // L2 only: the partials were written by other SMs in this launch
@@ -290,7 +338,7 @@ __device__ __forceinline__ bool exchange_with_peers(const CommParams &comm, uint
 		sum = tot;
 #endif
 	}
-	const bool cta_timed_out = __syncthreads_or(timed_out ? 1 : 0) != 0;
+	const bool cta_timed_out = main_sync_or(timed_out);
 	have_peer_counts = true;
 	total_count = 0.0f;
 	for (uint32_t r = 0; r < world; ++r)
@@ -309,19 +357,22 @@ template <int IN_MODE, bool MULTI>
 __global__ void __launch_bounds__(kTrainThreads, 1)
     nrc_train_kernel(const __grid_constant__ TrainParams tp, const __grid_constant__ CUtensorMap tm_w, const __grid_constant__ CUtensorMap tm_in) {
 	extern __shared__ uint8_t smem_raw[];
-	__shared__ float4 red_sm[3][16][16]; // reduction scratch: [block of the round][partial group][16 x float4 = 64 floats]
 	__shared__ float scratch[16];
 	__shared__ uint32_t peer_counts[NRC_MAX_RANKS];
 	uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	uint8_t *w_sm = smem + kWOff, *pool_sm = smem + kPoolOff, *delta_sm = pool_sm + tp.pool_tiles * 16384;
+	// reduction scratch [block of the round][partial group][16 x float4 = 64 floats] = 12 KB: lives in the delta buffers, which
+	// only the gradient phase uses (the producer warps, which may be a batch ahead, never touch them)
+	float4(*red_sm)[16][16] = (float4(*)[16][16])delta_sm;
 	uint64_t *bars = (uint64_t *)(delta_sm + 2 * 16384);
-	uint64_t *w_full = bars, *in_full = bars + 1, *df_full = bars + 2, *db_full = bars + 3, *dw1_done = bars + 4, *tile_done = bars + 5;
-	uint64_t *af_ready = bars + 6, *ab_ready = bars + 7, *d5_ready = bars + 8, *w_ready = bars + 9, *ds_ready = bars + 10;
-	uint32_t *tmem_slot = (uint32_t *)(bars + 11);
+	uint64_t *w_full = bars, *in_full = bars + 1 /* [2]: tile t uses in_full[t & 1] */, *df_full = bars + 3, *db_full = bars + 4, *dw1_done = bars + 5;
+	uint64_t *tile_done = bars + 6, *af_ready = bars + 7, *ab_ready = bars + 8, *d5_ready = bars + 9, *w_ready = bars + 10, *ds_ready = bars + 11;
+	uint32_t *tmem_slot = (uint32_t *)(bars + 12);
+	// hand-back of input buffers to the producer warps: (batch << 16 | rounds of the batch whose output-layer MMAs have completed),
+	// written by epilogue thread 0 - a counter, not a parity: a waiter can never miss a phase
+	volatile uint32_t *in_free = tmem_slot + 1;
 #ifdef NRC_TRACE
-	__shared__ uint2 gtrace[NRC_GTRACE_CAP];
-	__shared__ uint2 itrace[NRC_GTRACE_CAP];
-	uint32_t gtrace_n = 0, itrace_n = 0;
+	uint32_t gtrace_n = 0, itrace_n = 0, ptrace_n = 0;
 #endif
 	NRC_GTRACE(1);
 
@@ -331,9 +382,12 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	const uint32_t row = q * 32 + lane;
 
 	if (threadIdx.x == 0) {
-		mbar_init(w_full, 1), mbar_init(in_full, 1), mbar_init(df_full, 1), mbar_init(db_full, 1), mbar_init(dw1_done, 1), mbar_init(tile_done, 1);
+		mbar_init(w_full, 1), mbar_init(df_full, 1), mbar_init(db_full, 1), mbar_init(dw1_done, 1), mbar_init(tile_done, 1);
+		// an input tile arrives by TMA (one arrival + bytes) or as four quarter tiles from the producer warps
+		mbar_init(in_full, IN_MODE == NRC_IN_ENCODED ? 1 : 4), mbar_init(in_full + 1, IN_MODE == NRC_IN_ENCODED ? 1 : 4);
 		mbar_init(af_ready, kEpiWarps), mbar_init(ab_ready, kEpiWarps), mbar_init(d5_ready, kEpiWarps), mbar_init(w_ready, kEpiWarps);
 		mbar_init(ds_ready, kEpiWarps);
+		*in_free = 0u;
 		fence_mbar_init();
 	}
 	if (warp == kIssueWarp)
@@ -386,44 +440,35 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			*(uint4 *)(r + (((4 * h + c) ^ (row & 7)) << 4)) = make_uint4(o16[4 * c], o16[4 * c + 1], o16[4 * c + 2], o16[4 * c + 3]);
 	};
 
-	// this thread's half row of a_0 for record `tile * 128 + row` of batch `bp` (n = the batch's clamped record count)
-	auto encode_tile_row = [&](const GradParams &bp, uint64_t n, uint32_t tile, uint8_t *dst_tile) {
-		const uint64_t gi = (uint64_t)tile * NRC_TILE + row;
-		const bool valid = gi < n;
-		uint32_t o[16];
+	// Producer warps: this lane's whole row of a_0 for record `gi` of batch `bp` (n = the batch's clamped record count) as 32
+	// packed fp16 pairs. nrc_gradient.comp:27-34: an invalid record is a zero input with a zero target => exactly zero contribution
+	auto encode_record = [&](const GradParams &bp, uint64_t n, uint64_t gi, uint32_t o[32]) {
 #pragma unroll
-		for (int i = 0; i < 16; ++i)
-			o[i] = 0u; // nrc_gradient.comp:27-34: zero input + zero target => exactly zero contribution
+		for (int i = 0; i < 32; ++i)
+			o[i] = 0u;
+		if (gi >= n)
+			return;
 		if (IN_MODE == NRC_IN_PACKED) { // nrc_gradient.comp:29-31: UnpackNRCInput, then the same encoding
-			if (valid) {
-				float in[14];
-				uint32_t pk[4];
-				load_packed_input(bp.in, gi, bp.in_stride_bytes, pk);
-				unpack_nrc_input(bp.scene, pk, in);
-				encode_nrc_half(in, h, o);
-			}
+			float in[14];
+			uint32_t pk[4];
+			load_packed_input(bp.in, gi, bp.in_stride_bytes, pk);
+			unpack_nrc_input(bp.scene, pk, in);
+			encode_nrc(in, o);
 		} else if (IN_MODE == NRC_IN_UNPACKED) {
-			if (valid) {
-				float in[14];
-				const float2 *src = (const float2 *)((const uint8_t *)bp.in + gi * bp.in_stride_bytes);
+			float in[14];
+			const float2 *src = (const float2 *)((const uint8_t *)bp.in + gi * bp.in_stride_bytes);
 #pragma unroll
-				for (int i = 0; i < 7; ++i) {
-					const float2 t = __ldg(src + i);
-					in[2 * i] = t.x, in[2 * i + 1] = t.y;
-				}
-				encode_nrc_half(in, h, o);
+			for (int i = 0; i < 7; ++i) {
+				const float2 t = __ldg(src + i);
+				in[2 * i] = t.x, in[2 * i + 1] = t.y;
 			}
+			encode_nrc(in, o);
 		} else if (IN_MODE == NRC_IN_IMAGE_RANDOM) { // gradient.comp:47-49
 			uint32_t px = bp.seed_x + (uint32_t)(gi % 128u), py = bp.seed_y + (uint32_t)(gi / 128u);
 			pcg2d(px, py);
 			const float sc = 1.0f / (float)0xffffffffu;
-			if (valid)
-				encode_oneblob32_half(sc * (float)(h ? py : px), o);
+			encode_oneblob32(sc * (float)px, sc * (float)py, o);
 		}
-#if NRC_TRAIN_TS
-		tmem_st_x16(af_mine, o); // a_0 is also the forward stream's first TMEM operand (completion: tc_wait_st in arrive_ready below)
-#endif
-		store_half_row(dst_tile, o);
 	};
 	auto batch_count = [&](const GradParams &bp) -> uint64_t { // nrc_train_prepare.comp:17-18: count = min(count, capacity)
 		uint64_t n = bp.n;
@@ -439,26 +484,76 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	};
 
 	// mbarrier phase counters (every barrier completes once per use; the waiter tracks the parity of its next wait).
-	// Hand-offs: af_ready = a_k stored (forward epilogue k-1 or the input encoder) -> forward MMAs k; ab_ready = delta_l
+	// Hand-offs: in_full[t & 1] = a_0 of the CTA's t-th tile of the batch is in shared memory (TMA, or the four quarter tiles of
+	// the producer warps) -> forward MMAs 0; af_ready = a_k stored by forward epilogue k-1 -> forward MMAs k; ab_ready = delta_l
 	// stored by backward epilogue l+1 -> backward MMAs l; d5_ready = delta_5 stored by the forward epilogue of the output
 	// layer -> backward MMAs 5 of the next round (a barrier of its own: nothing orders it against the previous tile's
 	// last ab_ready phase); df_full / db_full = accumulator ready; dw1_done (pre-encoded inputs) = dW_1 has finished
-	// reading a_1, whose buffer the next TMA input tile overwrites.
+	// reading a_1, whose buffer the TMA load of the tile after next overwrites.
 	uint32_t df_ph = 0, db_ph = 0;            // epilogue threads
 	uint32_t af_ph = 0, ab_ph = 0, d5_ph = 0; // issuer
 	uint32_t ds_ph = 0;                       // issuer (TS form): delta_l is also in shared memory (dW_l's operand)
-	uint32_t in_ph = 0, dw1_ph = 0;           // issuer: TMA input tiles, dw1_done
+	uint32_t in_ph = 0, dw1_ph = 0;           // issuer: input tiles (bit j: parity of in_full[j]), dw1_done
 	uint32_t done_ph = 0;                     // epilogue threads: tile_done completes once per batch in which the CTA had tiles
 
-	// The first tile of a batch is encoded ahead of time: for batch 0 right here (while the weights stream in), for batch
-	// b + 1 at the end of batch b's gradient phase - before the grid barriers, the reduction and the weight reload, none of
-	// which the encoding depends on. It always goes to pool buffer 0 (the rotation below restarts with every batch).
+	if (warp >= kProducerWarp0) {
+		// ================================================================================== producer warps
+		// Record input modes: unit u = quarter (u & 3) of the CTA's tile t = u >> 2 of a batch (32 records, one per lane): raw
+		// record -> (UnpackNRCInput ->) the 64 encoded features -> the row's eight 16-byte chunks at their 128-byte-swizzle
+		// positions, exactly what TMA writes for pre-encoded inputs. The warps take the units round-robin and run AHEAD of the
+		// batch loop: tile t + 1 is produced during round t (forward of tile t, backward of tile t - 1) into the ring's spare
+		// buffer, the first tile of batch b + 1 while the other warps reduce batch b's gradient - the gather / encode latency
+		// (2 000 .. 6 000 cycles per tile) never sits between two rounds or in front of a grid barrier. They take no part in the
+		// CTA-wide barriers of the batch loop. A buffer is handed back through the counter in_free (see above).
+		if (IN_MODE != NRC_IN_ENCODED) {
+			const uint32_t pw = warp - kProducerWarp0;
+#pragma unroll 1
+			for (uint32_t b = 0; b < tp.num_batches; ++b) {
+				const GradParams &bp = tp.batch[b];
+				const uint64_t nb = batch_count(bp);
+				const uint32_t tiles_b = tiles_of_this_cta(nb);
+				TileRing ring;
+#pragma unroll 1
+				for (uint32_t t = 0; t < tiles_b; ++t) {
+					const uint32_t buf = t == 0 ? ring.fw[0] : ring.nx;
+					// tiles 0 and 1 go to buffers that are free once the previous batch's gradient phase (incl. the staged dW) is
+					// over; tile t >= 2 takes the buffer dW_1 of round t - 2 has read last - and its in_full barrier is the one of
+					// tile t - 2, which must have completed its phase before the first arrival of this one
+					const uint32_t need = (b << 16) | (t < 2 ? 0u : t - 1u);
+#pragma unroll 1
+					for (uint32_t qtr = 0; qtr < 4; ++qtr) {
+						if ((4 * t + qtr) % kProducerWarps != pw)
+							continue;
+						NRC_PTRACE(0x200 + t);
+						const uint32_t prow = qtr * 32 + lane;
+						uint32_t o[32];
+						encode_record(bp, nb, (uint64_t)(blockIdx.x + t * gridDim.x) * NRC_TILE + prow, o);
+						NRC_PTRACE(0x210 + t);
+						for (uint32_t spins = 0; (int32_t)(*in_free - need) < 0; ++spins) {
+							if (spins > (1u << 25))
+								__trap(); // a protocol bug must not hang the GPU (several seconds: longer than any peer time-out)
+							__nanosleep(100);
+						}
+						__threadfence_block();
+						uint8_t *dst = pool_sm + buf * 16384 + prow * 128;
+#pragma unroll
+						for (int c = 0; c < 8; ++c)
+							*(uint4 *)(dst + ((c ^ (prow & 7)) << 4)) = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+						fence_proxy_async_smem(); // generic-proxy stores -> visible to the MMA's async-proxy operand reads
+						__syncwarp();
+						if (lane == 0)
+							mbar_arrive(in_full + (t & 1));
+						NRC_PTRACE(0x220 + t);
+					}
+					if (t >= 1)
+						ring.rotate();
+				}
+			}
+		}
+	} else {
+	// ====================================================================================== warps 0..8: the batch loop
 	uint64_t n = batch_count(tp.batch[0]);
 	uint32_t my_tiles = tiles_of_this_cta(n);
-	if (IN_MODE != NRC_IN_ENCODED && warp < kEpiWarps && my_tiles) {
-		encode_tile_row(tp.batch[0], n, blockIdx.x, pool_sm);
-		arrive_ready(af_ready);
-	}
 	if (my_tiles == 0 && warp < kEpiWarps) {
 		// A CTA without a tile in batch 0 never issues the TMA weight load whose out-of-bounds fill pads W_5 from 3 to 64 rows
 		// (rows 323..383 of the weight tile): it writes those zeros itself, once. The same threads stage the weights in the
@@ -515,20 +610,10 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		//   forward  step k : D_F = a_k W_k^T               -> a_{k+1} = relu(D_F)   (k = 5: prediction -> loss gradient delta_5)
 		//   backward step l : D_B = delta_l W_l             -> delta_{l-1} = D_B * [a_l > 0]   (two delta buffers, ping-pong)
 		//                     dW_l += delta_l^T a_l          (accumulates in TMEM across all tiles of the CTA)
-		// Activation tiles live in a pool of eight 16 KB buffers: the forward tile holds a_0..a_{k+1}, the backward tile
-		// a_0..a_l, i.e. (k + 2) + (l + 1) = 8 at every step, and a buffer is handed over the moment its last reader is done:
-		//   a_{k+1} of a tile takes the buffer of a_{6-k} of the tile before it (k >= 1; freed by dW_{6-k} one step earlier),
-		//   a_0 / a_1 take the buffers of a_1 / a_0 two tiles back (freed by dW_1 / dW_0 at the end of the previous round).
-		// Every reuse is ordered by a tcgen05.commit that was issued after the last MMA reading the old contents.
+		// Activation tiles: see TileRing. Every reuse of a buffer is ordered by a tcgen05.commit that was issued after the last
+		// MMA reading the old contents.
 		// ---------------------------------------------------------------------------------------------------------------
-		uint32_t fw[6] = {0, 1, 2, 3, 4, 5}, bw[6] = {7, 6, 0, 0, 0, 0}; // pool buffers of the forward / backward tile's a_0..a_5
-		auto rotate_tiles = [&]() {
-			const uint32_t n0 = bw[1], n1 = bw[0], n2 = fw[5], n3 = fw[4], n4 = fw[3], n5 = fw[2];
-#pragma unroll
-			for (int i = 0; i < 6; ++i)
-				bw[i] = fw[i];
-			fw[0] = n0, fw[1] = n1, fw[2] = n2, fw[3] = n3, fw[4] = n4, fw[5] = n5;
-		};
+		TileRing ring;
 
 		if (my_tiles == 0) {
 			// nothing to do in the gradient phase: the reduction below only reads the partials of the CTAs that had a tile
@@ -541,9 +626,17 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 					for (int l = 0; l < NRC_LAYERS; ++l)
 						tma_load_2d(w_sm + l * 8192, &tm_w, 0, l * 64, w_full);
 				}
+				// pre-encoded inputs: a_0 of tile t arrives by TMA on in_full[t & 1] - tiles 0 and 1 right away, tile r + 1 at the
+				// start of round r into the ring's spare buffer: a whole round ahead (a TMA load from HBM takes 1 500+ cycles; issued
+				// at the end of the round before, as in the first version, the forward stream stood still for that long every round)
+				auto load_input_tile = [&](uint32_t t, uint32_t buf) {
+					mbar_arrive_expect_tx(in_full + (t & 1), 16384);
+					tma_load_2d(pool_sm + buf * 16384, &tm_in, 0, (int32_t)((blockIdx.x + t * gridDim.x) * NRC_TILE), in_full + (t & 1));
+				};
 				if (IN_MODE == NRC_IN_ENCODED) {
-					mbar_arrive_expect_tx(in_full, 16384);
-					tma_load_2d(pool_sm, &tm_in, 0, (int32_t)(blockIdx.x * NRC_TILE), in_full);
+					load_input_tile(0, ring.fw[0]);
+					if (my_tiles > 1)
+						load_input_tile(1, ring.nx);
 				}
 				if (b == 0)
 					mbar_wait(w_full, 0);
@@ -561,18 +654,18 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							d5_ph ^= 1;
 						}
 						if (has_f) { // ---- forward layer k of tile r
-							if (IN_MODE == NRC_IN_ENCODED && k == 0) {
-								mbar_wait(in_full, in_ph);
-								in_ph ^= 1;
+							if (k == 0) { // a_0 of tile r: in shared memory, by TMA or from the producer warps
+								mbar_wait(in_full + (r & 1), (in_ph >> (r & 1)) & 1u);
+								in_ph ^= 1u << (r & 1);
 							} else {
 								mbar_wait(af_ready, af_ph);
 								af_ph ^= 1;
 							}
 							tc_fence_after();
 							NRC_ITRACE(0x160 + k);
-							const uint32_t a_d = pool_desc + fw[k] * (16384 >> 4), b_d = w_desc + (uint32_t)(k * (8192 >> 4));
+							const uint32_t a_d = pool_desc + ring.fw[k] * (16384 >> 4), b_d = w_desc + (uint32_t)(k * (8192 >> 4));
 #if NRC_TRAIN_TS
-							if (!(IN_MODE == NRC_IN_ENCODED && k == 0)) { // a_k from tensor memory (pre-encoded a_0 arrives in shared memory by TMA)
+							if (k > 0) { // a_k from tensor memory (a_0 is in shared memory: SS form)
 #pragma unroll
 								for (int kk = 0; kk < 4; ++kk)
 									mma_ts_lh(df_issue, af_issue + kk * 8, b_d + kk * 2, dhi, k < 5 ? id_fwd64 : id_fwd16, kk > 0);
@@ -585,6 +678,14 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							}
 							tc_commit(df_full);
 							NRC_ITRACE(0x170 + k);
+							if (IN_MODE == NRC_IN_ENCODED && k == 0 && r >= 1 && r + 1 < my_tiles) {
+								// a_0 of tile r + 1 -> the spare buffer: the one of a_1 of tile r - 2, which dW_1 of the previous round read last
+								if (r >= 2) {
+									mbar_wait(dw1_done, dw1_ph);
+									dw1_ph ^= 1;
+								}
+								load_input_tile(r + 1, ring.nx);
+							}
 						}
 						if (has_b) { // ---- backward layer l of tile r - 1: dA first (critical path), then dW_l
 							if (l < 5) {
@@ -594,7 +695,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							tc_fence_after();
 							NRC_ITRACE(0x180 + l);
 							const uint32_t dl = del_desc + (uint32_t)(((5 - l) & 1) * (16384 >> 4));
-							const uint32_t al = pool_desc + bw[l] * (16384 >> 4), wl = w_desc + (uint32_t)(l * (8192 >> 4));
+							const uint32_t al = pool_desc + ring.bw[l] * (16384 >> 4), wl = w_desc + (uint32_t)(l * (8192 >> 4));
 							const uint32_t acc = (r > 1) ? 1u : 0u; // dW accumulates from the CTA's second tile on
 							const uint32_t dw_acc = tmem_addr(tmem, dw_lane(l), dw_col(l)); // dW_l's accumulator
 							if (l == 5) {
@@ -638,21 +739,13 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 									tc_commit(tile_done);
 								// (only where the wait below follows: every completed phase of dw1_done is consumed, so the
 								// waiter's parity can never drift from the barrier's - also across the batches of a launch)
-								if (IN_MODE == NRC_IN_ENCODED && l == 1 && has_f && r + 1 < my_tiles)
+								// (a_1's buffer becomes the spare of the next round, which the load of tile r + 2 fills)
+								if (IN_MODE == NRC_IN_ENCODED && l == 1 && r + 2 < my_tiles)
 									tc_commit(dw1_done);
 							}
 						}
-						if (IN_MODE == NRC_IN_ENCODED && k == 5 && r + 1 < my_tiles) {
-							// a_0 of tile r + 1 goes to the buffer of a_1 of tile r - 1 (bw[1]), free once dW_1 (step 4) has read it
-							if (has_b) {
-								mbar_wait(dw1_done, dw1_ph);
-								dw1_ph ^= 1;
-							}
-							mbar_arrive_expect_tx(in_full, 16384);
-							tma_load_2d(pool_sm + bw[1] * 16384, &tm_in, 0, (int32_t)((blockIdx.x + (r + 1) * gridDim.x) * NRC_TILE), in_full);
-						}
 					}
-					rotate_tiles();
+					ring.rotate();
 				};
 				issue_round(std::true_type{}, std::false_type{}, 0u);
 #pragma unroll 1
@@ -726,6 +819,10 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 						df_ph ^= 1;
 						tc_fence_after();
 						NRC_GTRACE(0x10 + k);
+						// the output layer's commit covers every MMA issued before it - dW_1 of this round's backward tile among
+						// them: its a_1 buffer is the next spare one (and the in_full barrier of tile r has long completed its phase)
+						if (IN_MODE != NRC_IN_ENCODED && k == 5 && threadIdx.x == 0)
+							*in_free = (b << 16) | (r + 1u);
 						if (k < NRC_HIDDEN_LAYERS) { // a_{k+1} = fp16(relu(D))
 							uint32_t v[32], o[16];
 							tmem_ld_x32(df_mine, v);
@@ -739,10 +836,10 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							NRC_GTRACE(0x20 + k);
 							// the shared-memory copy (dW_{k+1}'s operand and the ReLU mask of the backward pass) is off the chain: its first
 							// reader is issued after later arrivals of this warp, which order these stores and their proxy fence
-							store_half_row(pool_sm + fw[k + 1] * 16384, o);
+							store_half_row(pool_sm + ring.fw[k + 1] * 16384, o);
 							fence_proxy_async_smem();
 #else
-							store_half_row(pool_sm + fw[k + 1] * 16384, o);
+							store_half_row(pool_sm + ring.fw[k + 1] * 16384, o);
 							NRC_GTRACE(0x20 + k);
 							arrive_ready(af_ready);
 #endif
@@ -787,12 +884,6 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 #if NRC_TRAIN_TS
 							arrive_ready(ds_ready); // (both copies are complete here: the loss epilogue is not on a per-layer chain)
 #endif
-							if (IN_MODE != NRC_IN_ENCODED && r + 1 < my_tiles) {
-								// a_0 of tile r + 1 -> the buffer of a_1 of tile r - 1 (bw[1]): its last reader (dW_1, step 4) was issued
-								// before this step's forward MMAs, whose commit has just been observed
-								encode_tile_row(p, n, blockIdx.x + (r + 1) * gridDim.x, pool_sm + bw[1] * 16384);
-								arrive_ready(af_ready);
-							}
 						}
 					}
 					if (has_b && l >= 1) { // --------------------------------------------------- backward epilogue, layer l
@@ -804,7 +895,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 						uint32_t v[32], a[16], o[16];
 						tmem_ld_x32(db_mine, v);
 						{
-							const uint8_t *rr = pool_sm + bw[l] * 16384 + row * 128;
+							const uint8_t *rr = pool_sm + ring.bw[l] * 16384 + row * 128;
 #pragma unroll
 							for (int c = 0; c < 4; ++c) {
 								const uint4 t = *(const uint4 *)(rr + (((4 * h + c) ^ (row & 7)) << 4));
@@ -847,7 +938,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 									}
 								}
 							} else { // staging: the dead tile of a_{l+1} (its last reader was dW_{l+1} itself)
-								float *stage = (float *)(pool_sm + bw[l + 1] * 16384);
+								float *stage = (float *)(pool_sm + ring.bw[l + 1] * 16384);
 								stage_dw(l + 1, stage);
 								asm volatile("bar.sync 1, 256;" ::: "memory");
 								copy_layer(l + 1, stage);
@@ -856,8 +947,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 					}
 				}
 				if (last_round)
-					fin1 = bw[1], fin0 = bw[0];
-				rotate_tiles();
+					fin1 = ring.bw[1], fin0 = ring.bw[0];
+				ring.rotate();
 			};
 			epilogue_round(std::true_type{}, std::false_type{}, 0u);
 #pragma unroll 1
@@ -897,11 +988,12 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			}
 			NRC_GTRACE(8);
 		}
-		if (IN_MODE != NRC_IN_ENCODED && warp < kEpiWarps && tiles_next) { // encode the next batch's first tile now
+		if (IN_MODE != NRC_IN_ENCODED && warp < kEpiWarps) {
+			// this batch's gradient phase is over: the producer warps may fill the first input buffers of the next batch
 			if (my_tiles)
-				asm volatile("bar.sync 1, 256;" ::: "memory"); // every thread is done reading the staged dW (pool buffers 0 and 1)
-			encode_tile_row(tp.batch[b + 1], n_next, blockIdx.x, pool_sm);
-			arrive_ready(af_ready);
+				asm volatile("bar.sync 1, 256;" ::: "memory"); // every thread is done reading the staged dW (any pool buffer)
+			if (threadIdx.x == 0)
+				*in_free = (b + 1u) << 16;
 		}
 		w_reloads += (b > 0 && my_tiles) ? 1u : 0u;
 
@@ -983,7 +1075,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 					}
 				}
 				NRC_GTRACE(0x51);
-				__syncthreads();
+				main_sync();
 				if (!have_count) {
 					for (int w = 0; w < 8; ++w)
 						count += scratch[w];
@@ -1017,7 +1109,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 						adam_update(adam, my_i, my_entry, sum, total_count, st);
 					NRC_GTRACE(0x56);
 				}
-				__syncthreads();
+				main_sync();
 				NRC_GTRACE(0x57);
 			}
 			NRC_GTRACE(0x53);
@@ -1025,7 +1117,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 				const uint32_t cc = *p.d_count;
 				*p.d_count = cc < tp.batch_cap ? cc : tp.batch_cap;
 			}
-			if (adam_mode != 0 && __syncthreads_or(any_adam ? 1 : 0)) { // (the batch was not empty; identical on every CTA)
+			if (adam_mode != 0 && main_sync_or(any_adam)) { // (the batch was not empty; identical on every CTA; the barrier also
+				                                            // puts every thread's Adam stores in front of the state's publication)
 				if (b + 1 < tp.num_batches)
 					pending_state = st, publish_pending = true; // every CTA has read the old state once the next barrier is passed
 				else
@@ -1040,18 +1133,15 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		}
 		n = n_next, my_tiles = tiles_next;
 	}
-#ifdef NRC_TRACE
 	NRC_GTRACE(10);
-	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		for (uint32_t i = 0; i < gtrace_n; ++i)
-			g_nrc_gtrace[i] = gtrace[i];
+	} // warps 0..8
+#ifdef NRC_TRACE
+	if (blockIdx.x == 0 && threadIdx.x == 0)
 		g_nrc_gtrace_n = gtrace_n;
-	}
-	if (blockIdx.x == 0 && warp == kIssueWarp && itrace_n) { // (only the elected issuing thread has logged anything)
-		for (uint32_t i = 0; i < itrace_n; ++i)
-			g_nrc_itrace[i] = itrace[i];
+	if (blockIdx.x == 0 && warp == kIssueWarp && itrace_n) // (only the elected issuing thread has logged anything)
 		g_nrc_itrace_n = itrace_n;
-	}
+	if (blockIdx.x == 0 && threadIdx.x == kProducerWarp0 * 32)
+		g_nrc_ptrace_n = ptrace_n;
 #endif
 	tc_fence_before();
 	__syncthreads();
@@ -1070,7 +1160,7 @@ static cudaError_t launch_train_t(const TrainParams &p, const CUtensorMap &tm_w,
 		return e;
 	const uint64_t dev_bit = 1ull << (dev & 63);
 	if (!(configured.load(std::memory_order_acquire) & dev_bit)) {
-		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, train_smem_bytes(8));
+		cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, train_smem_bytes(kPoolMulti));
 		if (e != cudaSuccess)
 			return e;
 		configured.fetch_or(dev_bit, std::memory_order_release);
@@ -1100,7 +1190,7 @@ cudaError_t launch_train(const TrainParams &p, const CUtensorMap &tm_w, const CU
 	if (grid_out)
 		*grid_out = grid;
 	TrainParams q = p;
-	q.pool_tiles = ntiles > grid ? 8u : 6u; // two tiles in flight only where a CTA has more than one
+	q.pool_tiles = ntiles > grid ? kPoolMulti : kPoolSingle; // two tiles in flight (+ a spare input buffer) only where a CTA has more than one
 	const bool multi = p.comm.world > 1;
 	switch (p.batch[0].in_mode) {
 	case NRC_IN_ENCODED:
@@ -1124,6 +1214,7 @@ __global__ void __launch_bounds__(128) adam_kernel(const AdamParams a) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
 	if (i < NRC_WEIGHT_COUNT)
 		adam_update(a, i, a.entries[i], a.gradients[i], count, st);
+	__syncthreads();
 	publish_state_if_last(a, st);
 }
 
