@@ -311,7 +311,7 @@ def main():
     h_ev = torch.from_numpy(ev.view(np.uint8).reshape(-1)).pin_memory()
     e2e_steps = max(3, min(K, 20))
 
-    extra, train, multi = {}, {}, {}
+    extra, train, multi, stages = {}, {}, {}, {}
     with ClockSampler(local) as clocks:
         ms = timed(infer, K, W)
         value = world * n / (ms * 1e-3)
@@ -334,10 +334,25 @@ def main():
             ms_u = timed(lambda: st.infer_unpacked(rec, outputs=out), max(10, K // 4), 3)
             extra["infer_unpacked_queries_per_s"] = world * n / (ms_u * 1e-3)
             extra["infer_unpacked_ms_per_step"] = ms_u
+            # the encode stage on its own (nrc_encode_inputs: NRCInputEncode, 56 B in + 128 B out per record): HBM-bound
+            enc = torch.empty((n, 64), device=dev, dtype=torch.float16)
+            ms_enc = timed(lambda: nrc.encode_inputs(rec, out=enc), max(10, K // 4), 3)
+            gbs = n * (56 + 128) / (ms_enc * 1e-3) / 1e9
+            stages["encode_inputs"] = {"us": ms_enc * 1e3, "records_per_s": world * n / (ms_enc * 1e-3), "bytes_per_record": 56 + 128,
+                                       "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"]}}
+            # ... and the pre-encoded kernel on those features (what a renderer would feed it) next to the uniform-random headline input
+            extra["infer_encoded_from_encoded_records_ms_per_step"] = timed(lambda: st.infer_encoded(enc, out, clamp=True), max(10, K // 4), 3)
             del rec
             # the exact nrc_inference.comp pass (nrc_infer): 20-byte NRCEvalRecord per pixel + scene gather -> composite into the
             # rgba32f / rg32f screen images, from device records
             d_ev = h_ev.to(dev)
+            # record-streaming stage on its own (nrc_encode_packed_inputs: UnpackNRCInput gather + encode from the 20-byte eval records)
+            ms_pe = timed(lambda: nrc.encode_packed_inputs(d_ev[4:], scene, stride_bytes=20, n=n, out=enc), max(10, K // 4), 3)
+            gbs = n * (16 + 128) / (ms_pe * 1e-3) / 1e9
+            stages["unpack_encode_packed_inputs"] = {"us": ms_pe * 1e3, "records_per_s": world * n / (ms_pe * 1e-3), "bytes_per_record": 16 + 128,
+                                                     "roofline": {"bound": "hbm", "achieved": gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": gbs / peaks["hbm_gbs"],
+                                                                  "note": "algorithmic bytes only (record + encoded row); the scene gather itself is L1/L2 traffic (DESIGN 3.4)"}}
+            del enc
             d_bf = torch.rand((1080, 1920, 4), device=dev, generator=g)
             d_gb = torch.rand((1080, 1920, 2), device=dev, generator=g)
             d_trs = [torch.zeros(nrc.TRAIN_BATCH_SIZE * 40, dtype=torch.uint8, device=dev) for _ in range(4)]
@@ -461,7 +476,7 @@ def main():
                      "peak_source": f"{peaks['source']} cuBLAS bf16 burst (sustained {peaks['tflops_sustained']})",
                      "flop_per_query": FLOP_PER_QUERY,
                      "hbm_gbs_achieved": n * BYTES_PER_QUERY / (ms * 1e-3) / 1e9, "hbm_gbs_peak": peaks["hbm_gbs"]},
-        "train": train, "multi_gpu": multi, "extra": extra,
+        "train": train, "stages": stages, "multi_gpu": multi, "extra": extra,
     }
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1

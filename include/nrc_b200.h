@@ -134,6 +134,14 @@ uint64_t nrc_scene_prim_table_bytes(uint32_t prim_count);
 int nrc_scene_build_prim_table(const NrcScene *scene, uint32_t prim_count, void *d_prim_table, void *stream);
 int nrc_unpack_inputs(const void *d_packed_inputs, uint32_t stride_bytes, uint64_t n, const NrcScene *scene,
                       float *d_unpacked14, void *stream);
+/* NRCInputEncode on its own (NRCRecord.glsl:77-95): [n] records of 14 fp32 in UnpackedNRCInput order (position, scattered_dir,
+ * normal, roughness, diffuse, specular; `stride_bytes` >= 56 apart) -> [n][64] fp16 rows, the input layout of
+ * test/evaluate_NV.comp / nrc_infer_encoded / nrc_gradient_encoded. Same device function as the fused paths: bit-identical
+ * features. The *_packed form runs UnpackNRCInput (:98-125) in front of it, straight from PackedNRCInput words
+ * (`stride_bytes` 16 for bare inputs, 20 / 40 inside NRCEvalRecord / NRCTrainRecord buffers offset to their packed_input). */
+int nrc_encode_inputs(const void *d_inputs14, uint32_t stride_bytes, uint64_t n, void *d_encoded_f16x64, void *stream);
+int nrc_encode_packed_inputs(const void *d_packed_inputs, uint32_t stride_bytes, uint64_t n, const NrcScene *scene,
+                             void *d_encoded_f16x64, void *stream);
 int nrc_gradient(nrc_handle_t h, const void *d_train_records, uint32_t *d_count, uint32_t max_count,
                  const NrcScene *scene, void *stream);
 int nrc_train_batch(nrc_handle_t h, const void *d_train_records, uint32_t *d_count, uint32_t max_count,

@@ -81,6 +81,39 @@ def test_A5_fused_encoder_vs_reference_shader(nrc, g2):
     st.close()
 
 
+def test_A5_standalone_encoder_vs_reference_shader(nrc, g2):
+    """nrc_encode_inputs = NRCInputEncode as a kernel of its own: every feature, both signs, read directly (no network in
+    between). Same bounds as the fused encoder above - it is the same device function."""
+    ref = g2["glsl_encoded"].astype(np.float32)
+    got = nrc.encode_inputs(dev(g2["records14"])).float().cpu().numpy()
+    exact = [i for i in range(64) if not 36 <= i < 56]
+    assert np.array_equal(got[:, exact], ref[:, exact])
+    ulp16 = np.spacing(np.abs(ref[:, 36:52]).astype(np.float16)).astype(np.float32)
+    assert (np.abs(got[:, 36:52] - ref[:, 36:52]) <= np.maximum(ulp16, 2.5e-7)).all()
+    assert np.abs(got[:, 52:56] - ref[:, 52:56]).max() <= 2.0 ** -11
+
+
+@pytest.mark.parametrize("n", [1, 127, 129, 1000])
+def test_standalone_encoder_is_the_fused_encoder(nrc, g2, dscene, n):
+    """Encoding on its own and then the pre-encoded path == the fused record paths, bit for bit (ragged tile counts, strided
+    records); UnpackNRCInput + encode from packed words == nrc_unpack_inputs followed by nrc_encode_inputs, bit for bit."""
+    st = nrc.NrcState(0, (48, 32), seed=11)
+    rng = np.random.default_rng(n)
+    rec = np.concatenate([rng.uniform(-4, 4, (n, 3)), rng.uniform(0, 1, (n, 11))], axis=1).astype(np.float32)
+    enc = nrc.encode_inputs(dev(rec))
+    assert enc.shape == (n, 64) and enc.dtype == torch.float16
+    assert torch.equal(st.infer_encoded(enc), st.infer_unpacked(dev(rec)))
+    wide = np.zeros((n, 16), np.float32)  # 64-byte stride
+    wide[:, :14] = rec
+    assert torch.equal(nrc.encode_inputs(dev(wide), stride_bytes=64, n=n), enc)
+    m = min(n, g2["packed_inputs"].shape[0])
+    packed = dev(g2["packed_inputs"][:m])
+    a = nrc.encode_packed_inputs(packed, dscene)
+    b = nrc.encode_inputs(nrc.unpack_inputs(packed, dscene))
+    assert torch.equal(a, b)
+    st.close()
+
+
 def test_A1_A4_unpack_vs_reference_shader(nrc, g2, dscene):
     """UnpackNRCInput (NRCRecord.glsl:98-125): unorm16 decodes, barycentric interpolation through the index and transform
     buffers, face normal -> spherical, material / texture fetch. Tolerances: fp32 ulps of the quantity's range (positions

@@ -135,6 +135,8 @@ SIGNATURES = {
                             C.POINTER(C.c_void_p), C.c_void_p]),
     "nrc_infer_packed": (C.c_int, [C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrc_unpack_inputs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "nrc_encode_inputs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p]),
+    "nrc_encode_packed_inputs": (C.c_int, [C.c_void_p, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]),
     "nrc_gradient": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p]),
     "nrc_train_batch": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_int, C.c_void_p]),
     "nrc_train_frame": (C.c_int, [C.c_void_p, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_uint32, C.c_void_p, C.c_void_p]),
@@ -234,6 +236,24 @@ def unpack_inputs(packed_inputs, scene: "DeviceScene", stride_bytes: int = 16, n
     n = packed_inputs.numel() * packed_inputs.element_size() // stride_bytes if n is None else n
     out = torch.empty((n, 14), dtype=torch.float32, device=packed_inputs.device)
     _check(lib().nrc_unpack_inputs(_ptr(packed_inputs), stride_bytes, n, C.byref(scene.c), _ptr(out), _stream()))
+    return out
+
+
+def encode_inputs(records, stride_bytes: int = 56, n=None, out=None):
+    """NRCInputEncode (NRCRecord.glsl:77-95) as a kernel of its own: [n,14] fp32 records -> [n,64] fp16 features."""
+    import torch
+    n = records.numel() * records.element_size() // stride_bytes if n is None else n
+    out = torch.empty((n, 64), dtype=torch.float16, device=records.device) if out is None else out
+    _check(lib().nrc_encode_inputs(_ptr(records), stride_bytes, n, _ptr(out), _stream()))
+    return out
+
+
+def encode_packed_inputs(packed_inputs, scene: "DeviceScene", stride_bytes: int = 16, n=None, out=None):
+    """UnpackNRCInput + NRCInputEncode (NRCRecord.glsl:98-125, 77-95): PackedNRCInput words -> [n,64] fp16 features."""
+    import torch
+    n = packed_inputs.numel() * packed_inputs.element_size() // stride_bytes if n is None else n
+    out = torch.empty((n, 64), dtype=torch.float16, device=packed_inputs.device) if out is None else out
+    _check(lib().nrc_encode_packed_inputs(_ptr(packed_inputs), stride_bytes, n, C.byref(scene.c), _ptr(out), _stream()))
     return out
 
 

@@ -510,6 +510,60 @@ __global__ void __launch_bounds__(256) nrc_unpack_kernel(const void *packed, uin
 	for (int k = 0; k < 7; ++k)
 		dst[k] = make_float2(in[2 * k], in[2 * k + 1]);
 }
+// Stand-alone NRCInputEncode (NRCRecord.glsl:77-95), optionally behind UnpackNRCInput (:98-125): [n] records -> [n][64] fp16 in the
+// layout test/evaluate_NV.comp reads. The fused kernels never materialise this either; it is the encode / record-streaming
+// stage on its own - bound by HBM (56 or 16 B in, 128 B out per record; ~400 instructions per record hide under the traffic) -
+// and the producer of pre-encoded inputs for nrc_infer_encoded / nrc_gradient_encoded. One thread per record; the 128 x 128-byte
+// tile of a block is staged in shared memory (16-byte chunk c of row r at chunk position c ^ (r & 7): conflict-free both ways)
+// so that every warp-wide global store covers 512 contiguous bytes. The encoder is the very device function of the fused paths:
+// bit-identical features.
+template <int IN_MODE>
+__global__ void __launch_bounds__(128) nrc_encode_kernel(const void *in, uint32_t stride_bytes, uint64_t n, const NrcScene scene, uint4 *out) {
+	__shared__ __align__(128) uint4 tile[128 * 8];
+	const uint32_t t = threadIdx.x;
+	const uint64_t base = (uint64_t)blockIdx.x * 128, i = base + t;
+	uint32_t o[32];
+#pragma unroll
+	for (int k = 0; k < 32; ++k)
+		o[k] = 0u;
+	if (i < n) {
+		float f[14];
+		if (IN_MODE == NRC_IN_PACKED) {
+			uint32_t pk[4];
+			load_packed_input(in, i, stride_bytes, pk);
+			unpack_nrc_input(scene, pk, f);
+		} else {
+			const float2 *src = (const float2 *)((const uint8_t *)in + i * stride_bytes);
+#pragma unroll
+			for (int k = 0; k < 7; ++k) {
+				const float2 v = __ldg(src + k);
+				f[2 * k] = v.x, f[2 * k + 1] = v.y;
+			}
+		}
+		encode_nrc(f, o);
+	}
+#pragma unroll
+	for (int c = 0; c < 8; ++c)
+		tile[t * 8 + (c ^ (t & 7))] = make_uint4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+	__syncthreads();
+	const uint64_t rows = n - base < 128 ? n - base : 128; // rows of this tile that exist
+#pragma unroll
+	for (int k = 0; k < 8; ++k) {
+		const uint32_t idx = k * 128 + t, r = idx >> 3, c = idx & 7u; // a warp: 4 rows x 8 chunks = 512 contiguous bytes
+		if (r < rows)
+			out[base * 8 + idx] = tile[r * 8 + (c ^ (r & 7))];
+	}
+}
+cudaError_t launch_encode(const void *in, int in_mode, uint32_t stride_bytes, uint64_t n, const NrcScene &scene, void *out, cudaStream_t stream) {
+	if (n == 0)
+		return cudaSuccess;
+	const unsigned grid = (unsigned)((n + 127) / 128);
+	if (in_mode == NRC_IN_PACKED)
+		nrc_encode_kernel<NRC_IN_PACKED><<<grid, 128, 0, stream>>>(in, stride_bytes, n, scene, (uint4 *)out);
+	else
+		nrc_encode_kernel<NRC_IN_UNPACKED><<<grid, 128, 0, stream>>>(in, stride_bytes, n, scene, (uint4 *)out);
+	return cudaGetLastError();
+}
 // nrc_scene_build_prim_table: one thread per primitive copies what UnpackNRCInput would gather into its 64-byte row
 __global__ void __launch_bounds__(256) nrc_prim_table_kernel(const NrcScene scene, uint32_t prim_count, NrcPrimRow *rows) {
 	const uint32_t prim = blockIdx.x * blockDim.x + threadIdx.x;

@@ -145,6 +145,8 @@ cudaError_t launch_infer(const InferParams &p, const CUtensorMap &tm_w, const CU
 // cooperative launch: grid = min(#tiles of the largest batch, #SMs) CTAs, all co-resident
 cudaError_t launch_train(const TrainParams &p, const CUtensorMap &tm_w, const CUtensorMap &tm_in, int sms, cudaStream_t stream, uint32_t *grid_out = nullptr);
 cudaError_t launch_unpack(const void *packed, uint32_t stride_bytes, uint64_t n, const NrcScene &scene, float *out14, cudaStream_t stream);
+// NRCInputEncode as a kernel of its own: in_mode NRC_IN_UNPACKED (14-float records) or NRC_IN_PACKED (PackedNRCInput + scene) -> [n][64] fp16
+cudaError_t launch_encode(const void *in, int in_mode, uint32_t stride_bytes, uint64_t n, const NrcScene &scene, void *out, cudaStream_t stream);
 cudaError_t launch_prim_table(const NrcScene &scene, uint32_t prim_count, void *rows, cudaStream_t stream);
 cudaError_t launch_adam(const AdamParams &p, cudaStream_t stream);
 cudaError_t launch_sgd(const SgdParams &p, cudaStream_t stream);

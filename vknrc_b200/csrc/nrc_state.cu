@@ -744,6 +744,39 @@ int nrc_unpack_inputs(const void *d_packed_inputs, uint32_t stride_bytes, uint64
 	return NRC_OK;
 }
 
+int nrc_encode_inputs(const void *d_inputs14, uint32_t stride_bytes, uint64_t n, void *d_encoded_f16x64, void *stream) {
+	if (n == 0)
+		return NRC_OK;
+	NRC_REQUIRE(d_inputs14 && d_encoded_f16x64, "nrc_encode_inputs: null buffer");
+	NRC_REQUIRE(stride_bytes >= 56 && stride_bytes % 8 == 0 && ((uintptr_t)d_inputs14 & 7u) == 0 && ((uintptr_t)d_encoded_f16x64 & 15u) == 0,
+	            "nrc_encode_inputs: records 8-byte aligned with stride >= 56 (multiple of 8), encoded rows 16-byte aligned");
+	int rc = NRC_OK;
+	NrcState *s = scratch_state(&rc); // (the "is this an sm_100 device" check, done once per device)
+	if (!s)
+		return rc;
+	cudaError_t e = launch_encode(d_inputs14, NRC_IN_UNPACKED, stride_bytes, n, NrcScene{}, d_encoded_f16x64, (cudaStream_t)stream);
+	if (e != cudaSuccess)
+		return set_error(NRC_ERR_CUDA, std::string("nrc_encode_kernel: ") + cudaGetErrorString(e));
+	return NRC_OK;
+}
+int nrc_encode_packed_inputs(const void *d_packed_inputs, uint32_t stride_bytes, uint64_t n, const NrcScene *scene, void *d_encoded_f16x64, void *stream) {
+	if (n == 0)
+		return NRC_OK;
+	NRC_REQUIRE(d_packed_inputs && d_encoded_f16x64, "nrc_encode_packed_inputs: null buffer");
+	NRC_REQUIRE(stride_bytes >= 16 && stride_bytes % 4 == 0 && ((uintptr_t)d_packed_inputs & 3u) == 0 && ((uintptr_t)d_encoded_f16x64 & 15u) == 0,
+	            "nrc_encode_packed_inputs: inputs 4-byte aligned with stride >= 16 (multiple of 4), encoded rows 16-byte aligned");
+	int rc = check_scene(scene);
+	if (rc != NRC_OK)
+		return rc;
+	NrcState *s = scratch_state(&rc);
+	if (!s)
+		return rc;
+	cudaError_t e = launch_encode(d_packed_inputs, NRC_IN_PACKED, stride_bytes, n, *scene, d_encoded_f16x64, (cudaStream_t)stream);
+	if (e != cudaSuccess)
+		return set_error(NRC_ERR_CUDA, std::string("nrc_encode_kernel: ") + cudaGetErrorString(e));
+	return NRC_OK;
+}
+
 static void fill_record_batch(nrc_handle_t h, GradParams &p, const void *d_records, uint32_t *d_count, uint32_t max_count, const NrcScene *scene) {
 	p.n = max_count, p.d_count = d_count, p.in_mode = NRC_IN_PACKED, p.loss_kind = NRC_LOSS_RELATIVE_L2_LUMINANCE, p.loss_scale = NRC_LOSS_SCALE;
 	p.in = (const uint8_t *)d_records + offsetof(NrcTrainRecord, packed_input), p.in_stride_bytes = sizeof(NrcTrainRecord), p.scene = *scene;

@@ -784,7 +784,10 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 				}
 			};
 			uint32_t fin1 = 1, fin0 = 0;        // staging buffers of dW_1 / dW_0 (the last tile's a_1 / a_0 buffers)
-			float tgt[3] = {0.0f, 0.0f, 0.0f}; // the forward tile's target (loaded at step 0, used at step 5)
+			float tgt[3] = {0.0f, 0.0f, 0.0f}; // the forward tile's target (learn-an-image: sampled at step 0, used at step 5)
+			// record modes: the target's raw bits - requested at step 0, converted where they are used (step 5). A conversion next to
+			// the load made every epilogue warp sit out the load's whole latency at the start of each round (~1 000 cycles of 7 400)
+			uint32_t traw[3] = {0u, 0u, 0u};
 			bool valid_f = false;
 			uint64_t gi_f = 0;
 			auto epilogue_round = [&](auto HF, auto HB, uint32_t r) {
@@ -794,13 +797,14 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 					gi_f = (uint64_t)tile * NRC_TILE + row;
 					valid_f = gi_f < n;
 					tgt[0] = tgt[1] = tgt[2] = 0.0f;
+					traw[0] = traw[1] = traw[2] = 0u; // (+0.0 in either format)
 					if (h == 0 && valid_f && IN_MODE != NRC_IN_IMAGE_RANDOM) { // loaded first: the latency hides under the forward pass
 						if (p.target_is_f16) {
-							const __half *t = (const __half *)((const uint8_t *)p.target + gi_f * p.target_stride_bytes);
-							tgt[0] = __half2float(t[0]), tgt[1] = __half2float(t[1]), tgt[2] = __half2float(t[2]);
+							const uint16_t *t = (const uint16_t *)((const uint8_t *)p.target + gi_f * p.target_stride_bytes);
+							traw[0] = __ldg(t), traw[1] = __ldg(t + 1), traw[2] = __ldg(t + 2);
 						} else {
-							const float *t = (const float *)((const uint8_t *)p.target + gi_f * p.target_stride_bytes);
-							tgt[0] = t[0], tgt[1] = t[1], tgt[2] = t[2];
+							const uint32_t *t = (const uint32_t *)((const uint8_t *)p.target + gi_f * p.target_stride_bytes);
+							traw[0] = __ldg(t), traw[1] = __ldg(t + 1), traw[2] = __ldg(t + 2);
 						}
 					}
 					if (IN_MODE == NRC_IN_IMAGE_RANDOM && h == 0 && valid_f) { // target = the image at this sample's uv (gradient.comp:47-50)
@@ -837,7 +841,11 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							// the shared-memory copy (dW_{k+1}'s operand and the ReLU mask of the backward pass) is off the chain: its first
 							// reader is issued after later arrivals of this warp, which order these stores and their proxy fence
 							store_half_row(pool_sm + ring.fw[k + 1] * 16384, o);
-							fence_proxy_async_smem();
+							// (with a backward epilogue following in this step, its arrive_ready fences both copies: a fence of its own here
+							// made this warp sit out the drain of these stores before it could poll the backward accumulator's barrier)
+							if (!(has_b && l >= 1))
+								fence_proxy_async_smem();
+							NRC_GTRACE(0x60 + k);
 #else
 							store_half_row(pool_sm + ring.fw[k + 1] * 16384, o);
 							NRC_GTRACE(0x20 + k);
@@ -859,7 +867,10 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 								}
 #pragma unroll
 								for (int c = 0; c < 3; ++c) {
-									const float d = y[c] - tgt[c];
+									const float t = IN_MODE == NRC_IN_IMAGE_RANDOM ? tgt[c]
+									                : p.target_is_f16      ? __half2float(__ushort_as_half((unsigned short)traw[c]))
+									                                       : __uint_as_float(traw[c]);
+									const float d = y[c] - t;
 									g[c] = 2.0f * p.loss_scale * d * inv_den;
 									if (valid_f)
 										loss_acc += d * d * inv_den;
@@ -916,6 +927,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							NRC_GTRACE(0x40 + l);
 							store_half_row(delta_sm + ((6 - l) & 1) * 16384, o);
 							arrive_ready(ds_ready);
+							NRC_GTRACE(0x70 + l);
 						} else { // delta_0 only feeds dW_0
 							store_half_row(delta_sm + ((6 - l) & 1) * 16384, o);
 							NRC_GTRACE(0x40 + l);
