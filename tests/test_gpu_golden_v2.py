@@ -102,7 +102,7 @@ def test_standalone_encoder_is_the_fused_encoder(nrc, g2, dscene, n):
     rec = np.concatenate([rng.uniform(-4, 4, (n, 3)), rng.uniform(0, 1, (n, 11))], axis=1).astype(np.float32)
     enc = nrc.encode_inputs(dev(rec))
     assert enc.shape == (n, 64) and enc.dtype == torch.float16
-    assert torch.equal(st.infer_encoded(enc), st.infer_unpacked(dev(rec)))
+    assert torch.equal(st.infer_encoded(enc, clamp=True), st.infer_unpacked(dev(rec)))  # (the record paths clamp, nrc_inference.comp:46)
     wide = np.zeros((n, 16), np.float32)  # 64-byte stride
     wide[:, :14] = rec
     assert torch.equal(nrc.encode_inputs(dev(wide), stride_bytes=64, n=n), enc)
