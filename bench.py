@@ -256,6 +256,11 @@ def main():
     rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
     if args.impl == "reference":
         return run_reference(args, rank, world)
+    # stdout carries exactly ONE JSON line: libraries that write to fd 1 on their own (NCCL prints its version banner there when
+    # NCCL_DEBUG is set) are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
 
     import torch
     import torch.distributed as dist
@@ -494,7 +499,7 @@ def main():
     if world > 1 and multi and not multi.get("replicated_bit_identical", True):
         ok = False  # the data-parallel replicas diverged: this run is not a valid measurement
     if rank == 0:
-        print(json.dumps(line))
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
     if not ok:
