@@ -1,0 +1,3 @@
+#!/bin/bash
+nproc; lscpu | grep "Model name"
+python tools/probe_e2e_host.py 2>&1 | tail -6
