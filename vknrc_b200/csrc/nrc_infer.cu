@@ -263,7 +263,7 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 			uint32_t o[32];
 			encode_raw<IN_MODE>(p, gi, gi < n, raw, o, lut, textures);
 			if (it >= 2) { // the slot has finished layer 0 of the tile that used this buffer before
-				for (uint32_t spins = 0; in_free[2 * s + b] < (it >> 1); ++spins) {
+				for (uint32_t spins = 0; ld_acquire_cta(in_free + 2 * s + b) < (it >> 1); ++spins) {
 					if (spins > (1u << 22))
 						__trap(); // a protocol bug must not hang the GPU
 					__nanosleep(NRC_INFER_FREE_BACKOFF);
@@ -362,7 +362,7 @@ __global__ void __launch_bounds__((NT * 4 + NP) * 32, 1)
 							if (it + 2 < slot_tiles)
 								load_input_tile(it + 2);
 						} else {
-							in_free[2 * s + (it & 1)] = (it >> 1) + 1; // (this thread observed layer 0's completion one layer ago)
+							st_release_cta(in_free + 2 * s + (it & 1), (it >> 1) + 1); // (this thread observed layer 0's completion one layer ago)
 						}
 					}
 					NRC_TRACE_EV(s, NRC_TRACE_TAG(0));

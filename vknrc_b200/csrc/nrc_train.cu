@@ -529,7 +529,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 						uint32_t o[32];
 						encode_record(bp, nb, (uint64_t)(blockIdx.x + t * gridDim.x) * NRC_TILE + prow, o);
 						NRC_PTRACE(0x210 + t);
-						for (uint32_t spins = 0; (int32_t)(*in_free - need) < 0; ++spins) {
+						for (uint32_t spins = 0; (int32_t)(ld_acquire_cta(in_free) - need) < 0; ++spins) {
 							if (spins > (1u << 25))
 								__trap(); // a protocol bug must not hang the GPU (several seconds: longer than any peer time-out)
 							__nanosleep(100);
@@ -826,7 +826,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 						// the output layer's commit covers every MMA issued before it - dW_1 of this round's backward tile among
 						// them: its a_1 buffer is the next spare one (and the in_full barrier of tile r has long completed its phase)
 						if (IN_MODE != NRC_IN_ENCODED && k == 5 && threadIdx.x == 0)
-							*in_free = (b << 16) | (r + 1u);
+							st_release_cta(in_free, (b << 16) | (r + 1u));
 						if (k < NRC_HIDDEN_LAYERS) { // a_{k+1} = fp16(relu(D))
 							uint32_t v[32], o[16];
 							tmem_ld_x32(df_mine, v);
@@ -1005,7 +1005,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			if (my_tiles)
 				asm volatile("bar.sync 1, 256;" ::: "memory"); // every thread is done reading the staged dW (any pool buffer)
 			if (threadIdx.x == 0)
-				*in_free = (b + 1u) << 16;
+				st_release_cta(in_free, (b + 1u) << 16);
 		}
 		w_reloads += (b > 0 && my_tiles) ? 1u : 0u;
 

@@ -76,6 +76,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
 	__trap();
 }
 
+// A 32-bit counter in shared memory handed from one thread to pollers of the same CTA (buffer hand-backs that a parity wait
+// could miss): release store / acquire load at CTA scope, i.e. everything the storing thread did before is visible to a
+// poller that has seen the new value - and the pair is a synchronising access, not a data race, for the memory model and
+// for compute-sanitizer's racecheck.
+__device__ __forceinline__ void st_release_cta(volatile uint32_t *p, uint32_t v) {
+	asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32((const void *)p)), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_cta(const volatile uint32_t *p) {
+	uint32_t v;
+	asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32((const void *)p)) : "memory");
+	return v;
+}
+
 // ---------------------------------------------------------------------------------------------------------- proxies
 // generic-proxy writes to shared memory -> visible to the async proxy (TMA / tcgen05.mma operand reads)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
