@@ -58,6 +58,12 @@ def test_argument_errors_are_reported_not_thrown(L):
     # n == 0 is a no-op that needs no device
     assert L.nrc_mlp_evaluate_encoded(None, None, None, 0, None) == 0
     assert L.nrc_mlp_gradient_encoded(None, None, None, None, 0, None) == 0
+    # the stand-alone encode stage: empty input is a no-op, null buffers and a stride below one record are argument errors
+    assert L.nrc_encode_inputs(None, 56, 0, None, None) == 0
+    assert L.nrc_encode_inputs(None, 56, 10, None, None) != 0 and b"null" in L.nrc_last_error()
+    buf = (C.c_uint8 * 4096)()
+    assert L.nrc_encode_inputs(buf, 40, 4, buf, None) != 0 and b"stride" in L.nrc_last_error()
+    assert L.nrc_encode_packed_inputs(buf, 12, 4, None, buf, None) != 0
 
 
 def test_fails_loudly_without_a_gpu(L):
