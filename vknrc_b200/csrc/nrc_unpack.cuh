@@ -9,6 +9,15 @@
 
 namespace nrc {
 
+// One 256-bit read-only load (LDG.E.256 on sm_100): a 64-byte primitive row is two of them instead of four 128-bit loads. The
+// gather is bound by the number of divergent load instructions (every lane a line of its own: one L1 tag look-up per lane
+// and instruction), not by bytes: nrc_infer 131.1 -> 126.5 us at 1080p with the primitive row and the material read this way.
+__device__ __forceinline__ void ldg256(const void *p32_byte_aligned, float4 &a, float4 &b) {
+	asm volatile("ld.global.nc.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+	             : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+	             : "l"(p32_byte_aligned));
+}
+
 // sRGB -> linear for the 256 texel values: x <= 0.04045 ? x / 12.92 : ((x + 0.055) / 1.055)^2.4 with x = c / 255, evaluated
 // in double precision and rounded to fp32 (tools/gen_srgb_table.py). A table, as in the texture unit - powf per channel
 // per texel (24 per textured record) costs more than the whole MLP.
@@ -85,7 +94,8 @@ __device__ __forceinline__ void unpack_nrc_input(const NrcScene &sc, const uint3
 	uint32_t material_id;
 	if (sc.prim_table) { // one 64-byte row per primitive (nrc_scene_build_prim_table): four 16-byte loads, one level
 		const float4 *row = (const float4 *)sc.prim_table + 4 * (size_t)prim;
-		const float4 r0 = __ldg(row), r1 = __ldg(row + 1), r2 = __ldg(row + 2), r3 = __ldg(row + 3);
+		float4 r0, r1, r2, r3; // (the table is 64-byte aligned: nrc_scene_build_prim_table)
+		ldg256(row, r0, r1), ldg256(row + 2, r2, r3);
 		o[0][0] = r0.x, o[0][1] = r0.y, o[0][2] = r0.z, o[1][0] = r0.w, o[1][1] = r1.x, o[1][2] = r1.y, o[2][0] = r1.z, o[2][1] = r1.w, o[2][2] = r2.x;
 		tc[0][0] = r2.y, tc[0][1] = r2.z, tc[1][0] = r2.w, tc[1][1] = r3.x, tc[2][0] = r3.y, tc[2][1] = r3.z;
 		material_id = __float_as_uint(r3.w);
@@ -122,7 +132,11 @@ __device__ __forceinline__ void unpack_nrc_input(const NrcScene &sc, const uint3
 	out[5] = (nx == 0.0f && ny == 0.0f) ? 0.5f : 0.5f + atan2f(ny, nx) / (2.0f * kPi); // NRCSphEncode, :47-49
 	out[6] = acosf(fminf(fmaxf(nz, -1.0f), 1.0f)) / kPi;
 	const NrcMaterial *mat = sc.materials + material_id;
-	const float4 md = __ldg((const float4 *)mat), ms = __ldg((const float4 *)mat + 1);
+	float4 md, ms; // diffuse + texture id, specular + texture id: the first 32 bytes of the 64-byte std430 element
+	if (((uintptr_t)sc.materials & 31u) == 0u) // (uniform: a caller's buffer need only be 16-byte aligned)
+		ldg256(mat, md, ms);
+	else
+		md = __ldg((const float4 *)mat), ms = __ldg((const float4 *)mat + 1);
 	out[7] = __ldg(&mat->roughness);
 	const float u = tc[0][0] * bx + tc[1][0] * by + tc[2][0] * bz, w = tc[0][1] * bx + tc[1][1] * by + tc[2][1] * bz;
 	const uint32_t dtex = __float_as_uint(md.w), stex = __float_as_uint(ms.w);
