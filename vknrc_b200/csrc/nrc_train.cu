@@ -359,6 +359,10 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	extern __shared__ uint8_t smem_raw[];
 	__shared__ float scratch[16];
 	__shared__ uint32_t peer_counts[NRC_MAX_RANKS];
+	// every batch's record count (nrc_train_prepare.comp:17-18: min(count, capacity)), read once in the prologue: nothing in this
+	// launch changes a batch's count before that batch's own reduction phase (which only writes the clamped value back), and a
+	// dependent global load at the top of every batch iteration stood in front of the weight re-staging
+	__shared__ unsigned long long batch_n[NRC_TRAIN_BATCH_COUNT];
 	uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
 	uint8_t *w_sm = smem + kWOff, *pool_sm = smem + kPoolOff, *delta_sm = pool_sm + tp.pool_tiles * 16384;
 	// reduction scratch [block of the round][partial group][16 x float4 = 64 floats] = 12 KB: lives in the delta buffers, which
@@ -389,6 +393,18 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		mbar_init(ds_ready, kEpiWarps);
 		*in_free = 0u;
 		fence_mbar_init();
+	}
+	if (threadIdx.x >= 32 && threadIdx.x < 32 + NRC_TRAIN_BATCH_COUNT) {
+		const uint32_t bi = threadIdx.x - 32;
+		unsigned long long cnt = 0;
+		if (bi < tp.num_batches) {
+			cnt = tp.batch[bi].n;
+			if (tp.batch[bi].d_count) {
+				const unsigned long long c = *(volatile uint32_t *)tp.batch[bi].d_count;
+				cnt = c < cnt ? c : cnt;
+			}
+		}
+		batch_n[bi] = cnt;
 	}
 	if (warp == kIssueWarp)
 		tmem_alloc(tmem_slot, 512);
@@ -470,14 +486,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			encode_oneblob32(sc * (float)px, sc * (float)py, o);
 		}
 	};
-	auto batch_count = [&](const GradParams &bp) -> uint64_t { // nrc_train_prepare.comp:17-18: count = min(count, capacity)
-		uint64_t n = bp.n;
-		if (bp.d_count) {
-			const uint64_t c = *(volatile uint32_t *)bp.d_count;
-			n = c < n ? c : n;
-		}
-		return n;
-	};
+	auto batch_count = [&](uint32_t bi) -> uint64_t { return batch_n[bi]; };
 	auto tiles_of_this_cta = [&](uint64_t n) -> uint32_t {
 		const uint32_t ntiles = (uint32_t)((n + NRC_TILE - 1) / NRC_TILE);
 		return blockIdx.x < ntiles ? (ntiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -510,7 +519,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 #pragma unroll 1
 			for (uint32_t b = 0; b < tp.num_batches; ++b) {
 				const GradParams &bp = tp.batch[b];
-				const uint64_t nb = batch_count(bp);
+				const uint64_t nb = batch_count(b);
 				const uint32_t tiles_b = tiles_of_this_cta(nb);
 				TileRing ring;
 #pragma unroll 1
@@ -552,7 +561,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		}
 	} else {
 	// ====================================================================================== warps 0..8: the batch loop
-	uint64_t n = batch_count(tp.batch[0]);
+	uint64_t n = batch_count(0);
 	uint32_t my_tiles = tiles_of_this_cta(n);
 	if (my_tiles == 0 && warp < kEpiWarps) {
 		// A CTA without a tile in batch 0 never issues the TMA weight load whose out-of-bounds fill pads W_5 from 3 to 64 rows
@@ -574,7 +583,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		uint64_t n_next = 0;
 		uint32_t tiles_next = 0;
 		if (b + 1 < tp.num_batches) {
-			n_next = batch_count(tp.batch[b + 1]);
+			n_next = batch_count(b + 1);
 			tiles_next = tiles_of_this_cta(n_next);
 		}
 		if (b > 0 && my_tiles && warp < kEpiWarps) {
@@ -758,29 +767,56 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			// ================================================================================== epilogue warps
 			float loss_acc = 0.0f;
 			uint32_t valid_rows = 0;
-			// Draining a finished dW accumulator (M=64 TMEM layout: row r -> lane (r%16) + 32*(r/16)): TMEM -> fp32 staging
-			// in a dead pool buffer, 16-byte chunks XOR-swizzled per row against bank conflicts -> fully coalesced copy to
-			// this CTA's partial. For all but the last two layers this runs inside the backward pass of the CTA's last tile,
-			// in the time the epilogue warps would spend waiting for the next accumulator.
-			auto stage_dw = [&](int l, float *stage) {
+			// Draining a finished dW accumulator (M=64 TMEM layout: row r -> lane (r%16) + 32*(r/16)): every warp on its own - its 16
+			// rows x 32 columns go TMEM -> a 2 KB slice of a dead pool buffer (16-byte chunks XOR-swizzled per row against bank
+			// conflicts) -> this CTA's partial, each store instruction covering four 128-byte row segments. No CTA-wide barrier: the
+			// version that staged the whole layer and copied it with all 256 threads cost the backward chain of the CTA's last tile
+			// ~650 cycles per layer - every batch of a paper-sized frame - because a warp could not return to the chain before the
+			// slowest one had staged. (Unstaged stores straight from the registers were tried: 16-byte ones +4 us per frame - the
+			// partial sectors make the release fence of the grid barrier slow -, 32-byte ones +0.8 us.) For all but the last two layers this runs inside the backward
+			// pass of the CTA's last tile, in the time the epilogue warps would spend waiting for the next accumulator.
+			auto drain_dw = [&](int l, float *stage) {
 				uint32_t v[32];
 				tmem_ld_x32(tmem_addr(tmem, q * 32, dw_col(l) + 32 * h), v);
 				tc_wait_ld();
+				float4 *mine = (float4 *)stage + (q * 2 + h) * 128;
 				if ((lane & 16u) == dw_lane(l)) { // the 16 lanes of this quarter that hold dW_l's rows 16q .. 16q+15
-					const uint32_t r = q * 16 + (lane & 15u);
-					float4 *dst = (float4 *)(stage + r * 64);
+					const uint32_t rr = lane & 15u;
 #pragma unroll
 					for (int i = 0; i < 8; ++i)
-						dst[(8 * h + i) ^ (r & 7)] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
-						                                        __uint_as_float(v[4 * i + 3]));
+						mine[rr * 8 + (i ^ (rr & 7u))] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+						                                            __uint_as_float(v[4 * i + 3]));
+				}
+				__syncwarp();
+				float4 *out4 = (float4 *)(my_partial + l * 4096 + q * 16 * 64 + 32 * h);
+#pragma unroll
+				for (int it = 0; it < 4; ++it) {
+					const uint32_t idx = it * 32 + lane, rr = idx >> 3, c = idx & 7u;
+					out4[rr * 16 + c] = mine[rr * 8 + (c ^ (rr & 7u))];
 				}
 			};
-			auto copy_layer = [&](int l, const float *stage) { // 1024 float4 of dW_l: swizzled staging -> the partial
-				const float4 *stage4 = (const float4 *)stage;
-				float4 *out4 = (float4 *)my_partial + l * 1024;
-				for (uint32_t idx = threadIdx.x; idx < 1024; idx += kEpiThreads) {
-					const uint32_t r = (idx >> 4) & 63u;
-					out4[idx] = stage4[(idx & ~15u) | ((idx & 15u) ^ (r & 7u))];
+			// Two accumulators that share their TMEM columns (dW_le in lanes 0..15, dW_le+1 in lanes 16..31 of every quarter, le even)
+			// drained by ONE tcgen05.ld: every lane stages a row, the warp copies both layers' slices.
+			auto drain_two = [&](int le, float *stage_e, float *stage_o) {
+				uint32_t v[32];
+				tmem_ld_x32(tmem_addr(tmem, q * 32, dw_col(le) + 32 * h), v);
+				tc_wait_ld();
+				const uint32_t slice = (q * 2 + h) * 128, rr0 = lane & 15u;
+				float4 *mine = (float4 *)((lane & 16u) ? stage_o : stage_e) + slice;
+#pragma unroll
+				for (int i = 0; i < 8; ++i)
+					mine[rr0 * 8 + (i ^ (rr0 & 7u))] = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+					                                              __uint_as_float(v[4 * i + 3]));
+				__syncwarp();
+#pragma unroll
+				for (int o = 0; o < 2; ++o) {
+					const float4 *src = (const float4 *)(o ? stage_o : stage_e) + slice;
+					float4 *out4 = (float4 *)(my_partial + (le + o) * 4096 + q * 16 * 64 + 32 * h);
+#pragma unroll
+					for (int it = 0; it < 4; ++it) {
+						const uint32_t idx = it * 32 + lane, rr = idx >> 3, c = idx & 7u;
+						out4[rr * 16 + c] = src[rr * 8 + (c ^ (rr & 7u))];
+					}
 				}
 			};
 			uint32_t fin1 = 1, fin0 = 0;        // staging buffers of dW_1 / dW_0 (the last tile's a_1 / a_0 buffers)
@@ -949,11 +985,14 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 										dst[0] = __uint_as_float(v5[0]), dst[64] = __uint_as_float(v5[1]), dst[128] = __uint_as_float(v5[2]);
 									}
 								}
-							} else { // staging: the dead tile of a_{l+1} (its last reader was dW_{l+1} itself)
-								float *stage = (float *)(pool_sm + ring.bw[l + 1] * 16384);
-								stage_dw(l + 1, stage);
-								asm volatile("bar.sync 1, 256;" ::: "memory");
-								copy_layer(l + 1, stage);
+							} else if (l == 3) { // dW_4 (its column partner dW_5^T went out a step ago); staging: the dead tile of a_4
+								NRC_GTRACE(0x80 + l);
+								drain_dw(4, (float *)(pool_sm + ring.bw[4] * 16384));
+								NRC_GTRACE(0x90 + l);
+							} else if (l == 1) { // dW_2 (final now) together with dW_3 (final since the step before): they share columns
+								NRC_GTRACE(0x80 + l);
+								drain_two(2, (float *)(pool_sm + ring.bw[2] * 16384), (float *)(pool_sm + ring.bw[3] * 16384));
+								NRC_GTRACE(0x90 + l);
 							}
 						}
 					}
@@ -967,17 +1006,14 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			for (uint32_t r = 1; r < my_tiles; ++r)
 				epilogue_round(std::true_type{}, std::true_type{}, r);
 			epilogue_round(std::false_type{}, std::true_type{}, my_tiles);
-			// ---- the last two layers' dW complete with tile_done (dW_5..dW_2 were drained during the backward pass); they are
-			// staged in the last tile's a_1 / a_0 buffers (dead once every MMA has completed, and distinct from the buffers
-			// the earlier drains may still be copied out of by slower warps)
+			// ---- the last two layers' dW complete with tile_done (dW_5..dW_2 were drained during the backward pass); their
+			// staging slices are in the last tile's a_1 / a_0 buffers (dead once every MMA has completed)
 			NRC_GTRACE(5);
 			mbar_wait(tile_done, done_ph);
 			done_ph ^= 1;
 			tc_fence_after();
 			NRC_GTRACE(6);
-			float *stage1 = (float *)(pool_sm + fin1 * 16384), *stage0 = (float *)(pool_sm + fin0 * 16384);
-			stage_dw(1, stage1);
-			stage_dw(0, stage0);
+			drain_two(0, (float *)(pool_sm + fin0 * 16384), (float *)(pool_sm + fin1 * 16384));
 			// loss / count slots: fixed-order reduction over the four h == 0 warps (deterministic)
 			float cnt = (float)valid_rows;
 #pragma unroll
@@ -990,8 +1026,6 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			tc_fence_before();
 			asm volatile("bar.sync 1, 256;" ::: "memory");
 			NRC_GTRACE(7);
-			copy_layer(1, stage1);
-			copy_layer(0, stage0);
 			if (threadIdx.x < (NRC_GRAD_STRIDE - NRC_WEIGHT_COUNT) / 4) { // loss, count, zero padding
 				float4 v = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 				if (threadIdx.x == 0)
@@ -1002,8 +1036,8 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		}
 		if (IN_MODE != NRC_IN_ENCODED && warp < kEpiWarps) {
 			// this batch's gradient phase is over: the producer warps may fill the first input buffers of the next batch
-			if (my_tiles)
-				asm volatile("bar.sync 1, 256;" ::: "memory"); // every thread is done reading the staged dW (any pool buffer)
+			// (thread 0 is past the barrier above, which every epilogue warp reaches after its last drain: nothing reads the
+			// pool buffers any more)
 			if (threadIdx.x == 0)
 				st_release_cta(in_free, (b + 1u) << 16);
 		}
