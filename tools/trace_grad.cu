@@ -2,7 +2,8 @@
 // prints CTA 0 / thread 0's event timeline (tags: 1 entry, 2 setup done, 3 inputs ready, 0x1l fwd accumulator l ready,
 // 0x2l fwd epilogue l stored, 0x3l dA accumulator ready, 0x4l delta stored, 5 tile loop done, 6 dW complete, 7 dW
 // staged, 8 partial written, 9 grid barrier passed, 0x50-0x54 reduction (0x51 partials loaded, 0x58/0x52 tree, 0x55 gradient stored,
-// 0x56 Adam done, 0x57 CTA barrier), 10 exit).
+// 0x56 Adam done, 0x57 CTA barrier), 0x59 second grid barrier passed, 0x5A weights re-staged, 0x6k forward copy of layer k issued,
+// 0x7l delta_l-1 copy stored + arrived, 0x8l / 0x9l drain of a finished dW accumulator started / done, 10 exit).
 #include "../vknrc_b200/csrc/nrc_train.cu"
 #include <cstdio>
 #include <climits>

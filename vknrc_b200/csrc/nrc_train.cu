@@ -609,6 +609,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 			__syncwarp();
 			if (lane == 0)
 				mbar_arrive(w_ready);
+			NRC_GTRACE(0x5A);
 		}
 
 		// ---------------------------------------------------------------------------------------------------------------
@@ -1174,6 +1175,7 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		NRC_GTRACE(0x54);
 		if (b + 1 < tp.num_batches) {
 			grid_sync<false>(tp.grid_bar, bar_target); // the next batch runs on the weights (and optimizer state) just written
+			NRC_GTRACE(0x59);
 			if (publish_pending && blockIdx.x == 0 && threadIdx.x == 0)
 				*tp.adam.opt_state = pending_state; // read again only after the next batch's first grid barrier
 		}
