@@ -368,6 +368,7 @@ def main():
             extra["infer_eval_records_scatter_tflops_per_gpu"] = n * FLOP_PER_QUERY / (ms_r * 1e-3) / 1e12
             ms_p = timed(lambda: st.infer_packed(d_ev[4:], scene, outputs=out, stride_bytes=20, max_count=n), max(10, K // 4), 3)
             extra["infer_eval_records_f16_ms_per_step"] = ms_p
+            d_bf2, d_gb2 = d_bf, d_gb
             del d_bf, d_gb
 
             # ---- training (the other half of the metric). One frame = 4 dependent batches of 16384 records (configs[3]).
@@ -390,6 +391,11 @@ def main():
             # the same frame on 40-byte NRCTrainRecord buffers (scene gather fused), the reference's NNTrain input
             d_trec = [torch.from_numpy(synth.train_records(100 + 10 * rank + b, nb, 20000, 8).view(np.uint8).reshape(-1)).to(dev) for b in range(4)]
             ms_tr = timed(lambda: st.train_frame(d_trec, scene, max_count=nb), max(40, K // 2), 5)
+            # the whole NRC step of one rendered frame as the reference schedules it (NRCRenderGraph.cpp:46-80): nrc_inference over
+            # the frame's eval records (composite + train-record feedback), then the four training batches - ONE nrc_frame call
+            tr_c = [torch.full((1,), nb, dtype=torch.int32, device=dev) for _ in range(4)]
+            ms_f = timed(lambda: st.frame(d_ev, cnt, scene, d_bf2, d_gb2, 1920, d_trec, tr_c, max_eval_count=n), max(20, K // 4), 3)
+            extra["nrc_frame_1080p_eval_plus_4x16384_train_us"] = ms_f * 1e3
             train.update({
                 "records_per_s": world * 4 * nb / (ms_t * 1e-3), "unit": "records/s", "scaling": "weak",
                 "records_per_gpu_per_frame": 4 * nb, "frame_us": ms_t * 1e3, "frame_us_from_train_records": ms_tr * 1e3,
