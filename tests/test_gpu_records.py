@@ -108,6 +108,13 @@ def test_full_size_record_inference_properties(nrc, oracle_mod):
     yu = st.infer_unpacked(unp)
     assert torch.equal(yu, y)
     assert torch.equal(st.infer_unpacked(unp[perm].contiguous()), yu[perm])
+    # the encode stage on its own at the same size: rows permute with the records, both record forms give the same rows, and
+    # the pre-encoded path on them is the fused path, bit for bit
+    enc = nrc.encode_inputs(unp)
+    assert torch.equal(nrc.encode_inputs(unp[perm].contiguous()), enc[perm])
+    assert torch.equal(nrc.encode_packed_inputs(pk, dsc), enc)
+    assert torch.equal(st.infer_encoded(enc, clamp=True), y)
+    del enc
     idx = torch.randint(0, n, (2048,), device="cuda", generator=g)
     sub = pk[idx].cpu().numpy().view(np.uint32)
     ref = oracle_mod.evaluate(w32.astype(np.float16), oracle_mod.encode(oracle_mod.unpack(sc, sub)), oracle_mod.ACC_FP32, clamp=True)
