@@ -936,22 +936,20 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 					}
 					if (has_b && l >= 1) { // --------------------------------------------------- backward epilogue, layer l
 						// delta_{l-1} = fp16(D) * [a_l > 0], NaN -> 0 (NN_nv.glsl:198-220, 240-242)
-						uint32_t v[32], a[16], o[16];
-						{ // a_l of this thread's half row (the ReLU mask): requested BEFORE the wait for the accumulator - the tile has been in
-						  // shared memory since the forward pass, and behind the wait these loads queued up with dW's operand reads
-							const uint8_t *rr = pool_sm + ring.bw[l] * 16384 + row * 128;
-#pragma unroll
-							for (int c = 0; c < 4; ++c) {
-								asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
-								             : "=r"(a[4 * c]), "=r"(a[4 * c + 1]), "=r"(a[4 * c + 2]), "=r"(a[4 * c + 3])
-								             : "r"(smem_u32(rr + (((4 * h + c) ^ (row & 7)) << 4))));
-							}
-						}
 						mbar_wait(db_full, db_ph);
 						db_ph ^= 1;
 						tc_fence_after();
 						NRC_GTRACE(0x30 + l);
+						uint32_t v[32], a[16], o[16];
 						tmem_ld_x32(db_mine, v);
+						{
+							const uint8_t *rr = pool_sm + ring.bw[l] * 16384 + row * 128;
+#pragma unroll
+							for (int c = 0; c < 4; ++c) {
+								const uint4 t = *(const uint4 *)(rr + (((4 * h + c) ^ (row & 7)) << 4));
+								a[4 * c] = t.x, a[4 * c + 1] = t.y, a[4 * c + 2] = t.z, a[4 * c + 3] = t.w;
+							}
+						}
 						tc_wait_ld();
 #pragma unroll
 						for (int i = 0; i < 16; ++i) {
