@@ -339,15 +339,23 @@ int NrcState::host_pipeline(const void *h_in, uint32_t in_bytes, void *h_out, ui
 		NRC_CUDA_TRY(cudaMalloc(&m_stage_out, n * out_bytes), sink);
 		m_stage_in_bytes = n * in_bytes, m_stage_out_bytes = n * out_bytes;
 	}
-	// equal chunks of whole 128-query tiles (the host -> device copies are the long pole: everything else hides under them)
+	// chunks of whole 128-query tiles. The host -> device copies are the long pole and everything else hides under them - except
+	// what follows the LAST copy (that chunk's kernel and device -> host copy): shrinking chunks (16 16 12 8 6 3 2 1
+	// sixty-fourths). Measured on a 1080p frame of 20-byte records (bare 41.5 MB copy: 0.75 ms): eight equal chunks 0.861 ms,
+	// this table 0.852, five / four / three / two tapered chunks 0.854 / 0.866 / 0.894 / 1.08 ms (a chunk's device -> host
+	// copy only overlaps the host -> device copies of LATER chunks)
+	static constexpr uint32_t kCum64[] = {0, 16, 32, 44, 52, 58, 61, 63, 64};
+	constexpr int kTaperChunks = (int)(sizeof(kCum64) / sizeof(kCum64[0])) - 1;
+	static_assert(kTaperChunks >= 1 && kTaperChunks <= kHostChunks, "one event pair per chunk");
 	const uint64_t tiles = (n + NRC_TILE - 1) / NRC_TILE;
-	const int chunks = (int)(tiles < (uint64_t)kHostChunks ? tiles : (uint64_t)kHostChunks);
+	const bool tapered = tiles >= 64 * 8; // (small inputs: equal chunks, at most one per tile)
+	const int chunks = tapered ? kTaperChunks : (int)(tiles < (uint64_t)kHostChunks ? tiles : (uint64_t)kHostChunks);
 	NRC_CUDA_TRY(cudaEventRecord(m_ev_start, stream), sink);
 	NRC_CUDA_TRY(cudaStreamWaitEvent(m_stream_in, m_ev_start, 0), sink);
 	NRC_CUDA_TRY(cudaStreamWaitEvent(m_stream_out, m_ev_start, 0), sink);
 	uint64_t first = 0;
 	for (int c = 0; c < chunks; ++c) {
-		const uint64_t last_tile = tiles * (uint64_t)(c + 1) / (uint64_t)chunks;
+		const uint64_t last_tile = tapered ? tiles * kCum64[c + 1] / 64 : tiles * (uint64_t)(c + 1) / (uint64_t)chunks;
 		const uint64_t end = last_tile * NRC_TILE < n ? last_tile * NRC_TILE : n, cnt = end - first;
 		uint8_t *d_in = (uint8_t *)m_stage_in + first * in_bytes, *d_out = (uint8_t *)m_stage_out + first * out_bytes;
 		NRC_CUDA_TRY(cudaMemcpyAsync(d_in, (const uint8_t *)h_in + first * in_bytes, cnt * in_bytes, cudaMemcpyHostToDevice, m_stream_in), sink);
