@@ -86,6 +86,15 @@ public:
 		scene.prim_table = table;
 	}
 
+	// NRCInputEncode as a stage of its own (NRCRecord.glsl:77-95, behind UnpackNRCInput :98-125 for packed records):
+	// -> [n][64] fp16 rows, the input layout of test/evaluate_NV.comp / nrc_infer_encoded / nrc_gradient_encoded
+	static void EncodeInputs(const void *inputs14, uint32_t stride_bytes, uint64_t n, void *encoded, void *stream) {
+		Check(nrc_encode_inputs(inputs14, stride_bytes, n, encoded, stream));
+	}
+	static void EncodePackedInputs(const void *packed_inputs, uint32_t stride_bytes, uint64_t n, const NrcScene &scene, void *encoded, void *stream) {
+		Check(nrc_encode_packed_inputs(packed_inputs, stride_bytes, n, &scene, encoded, stream));
+	}
+
 	// the NNInference pass (nrc_inference.comp): queries -> use_weights MLP -> screen composite / train-record feedback
 	void Infer(const FrameBuffers &f, const NrcScene &scene, void *stream) {
 		Check(nrc_infer(m_handle, f.eval_records, f.eval_count, f.max_eval_count, &scene, f.bias_factor_r, f.factor_gb, f.image_pitch,
