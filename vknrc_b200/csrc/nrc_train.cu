@@ -14,13 +14,16 @@
 //     a_l      [sample][in]  used K-major  (forward A)   and MN-major (dW: B with K = sample)
 //     delta_l  [sample][out] used K-major  (dA: A)       and MN-major (dW: A with K = sample)
 //   so each tensor is stored once and read through two UMMA descriptor flavours - no transposes, no copies.
-//   forward  l=0..5 : D[128 x 64|16] = a_l * W_l^T                  (M=128)  -> ReLU -> a_{l+1}         (TMEM -> smem)
+//   forward  l=0..5 : D[128 x 64|16] = a_l * W_l^T                  (M=128)  -> ReLU -> a_{l+1}: fp16 back into TENSOR memory as the
+//                     next layer's A operand (TS-form MMAs; layer 0 reads a_0 from shared memory), plus a shared-memory copy for dW
 //   loss            : delta_5 = dL/dy (NN_nv.glsl:162-196)
-//   backward l=5..1 : D[128 x 64]   = delta_l * W_l                 (M=128)  -> * [a_l > 0] -> delta_{l-1}
-//   dW       l=5..0 : dW_l[64 x 64] += delta_l^T * a_l  (K = 128 samples, M=64) accumulated IN TMEM across all of the
-//                     CTA's tiles (5*64 + 16 fp32 columns), written once per CTA as a partial.
-//   Hand-offs are mbarriers only: a_ready (8 warp arrivals: operand stored + accumulator drained -> issuer),
-//   d_full (tcgen05.commit -> epilogue warps), tile_done (all MMAs of the CTA's last tile of a batch complete).
+//   backward l=5..1 : D[128 x 64]   = delta_l * W_l                 (M=128, A from tensor memory)  -> * [a_l > 0] -> delta_{l-1}
+//   dW       l=5..0 : dW_l[64 x 64] += delta_l^T * a_l  (K = 128 samples, M=64, both operands from shared memory) accumulated IN TMEM
+//                     across all of the CTA's tiles (two M=64 accumulators share 64 columns at lane offsets 0 / 16: 192 columns),
+//                     written once per CTA as a partial.
+//   Hand-offs are mbarriers only: af_ready / ab_ready (8 warp arrivals: TMEM operand stored + accumulator drained -> issuer),
+//   ds_ready (the shared-memory copy of delta_l is complete -> dW_l), df_full / db_full (tcgen05.commit -> epilogue warps),
+//   tile_done (all MMAs of the CTA's last tile of a batch complete).
 // Then, in the same launch: grid barrier -> the partials are summed in a fixed order (deterministic, unlike the
 // reference's 2.6 M fp32 atomics per batch, NN_nv.glsl:309-314,357-364), each CTA owning a slice of the 20 736 floats,
 // and (optionally) nrc_optimize.comp is applied verbatim to that slice -> grid barrier -> next batch of the frame.
@@ -72,9 +75,6 @@ __device__ unsigned int g_nrc_ptrace_n;
 #ifndef NRC_COMM_POLL_PARALLEL
 #define NRC_COMM_POLL_PARALLEL 0
 #endif
-#ifndef NRC_TRAIN_TS
-#define NRC_TRAIN_TS 1 // 0: the round-1 form (all operands from shared memory, dW accumulators side by side)
-#endif
 
 namespace nrc {
 
@@ -88,7 +88,6 @@ constexpr uint32_t kPoolOff = NRC_LAYERS * 8192;      // P x 16 KB activation ti
 constexpr uint32_t kPoolMulti = 9, kPoolSingle = 6;
 constexpr uint32_t train_smem_bytes(uint32_t pool_tiles) { return kPoolOff + (pool_tiles + 2) * 16384 + 256 + 1024; }
 static_assert(train_smem_bytes(kPoolMulti) + 256 <= 232448, "dynamic + static shared memory of a CTA");
-#if NRC_TRAIN_TS
 // TMEM map (columns x lanes): the M=64 dW accumulators occupy 16 of every 32 lanes, so two of them share 64 columns - dW_l at
 // columns 64*(l/2), lane offset 16*(l%2) (dW_4 with dW_5^T) - 192 columns instead of 336. That leaves room for the fp16 A
 // operands of both streams in TMEM: forward (a_k) and back-propagation (delta_l) run TS-form, 32 instead of 50.8 cycles per
@@ -97,12 +96,6 @@ constexpr uint32_t kColWorkF = 192, kColWorkB = 256;  // working accumulators of
 constexpr uint32_t kColAF = 320, kColAB = 352;        // fp16 A operands (32 columns = 64 fp16 per lane): a_k / delta_l
 __device__ __forceinline__ constexpr uint32_t dw_col(int l) { return l == 5 ? 128u : 64u * (uint32_t)(l >> 1); }
 __device__ __forceinline__ constexpr uint32_t dw_lane(int l) { return l == 5 ? 16u : 16u * (uint32_t)(l & 1); }
-#else
-constexpr uint32_t kColDW5 = 320;                     // TMEM columns: dW_l at 64*l, dW_5^T at 320,
-constexpr uint32_t kColWorkF = 384, kColWorkB = 448;  // working accumulators of the forward / backward stream
-__device__ __forceinline__ constexpr uint32_t dw_col(int l) { return l == 5 ? kColDW5 : 64u * (uint32_t)l; }
-__device__ __forceinline__ constexpr uint32_t dw_lane(int) { return 0u; }
-#endif
 constexpr uint32_t kEpiWarps = 8, kEpiThreads = 256, kIssueWarp = 8;
 constexpr uint32_t kProducerWarp0 = 9, kProducerWarps = 3; // record input modes: raw record -> a_0, a tile ahead of the forward pass
 constexpr int kMainThreads = 288;                           // warps 0..8: every CTA-wide barrier of the batch loop (named barrier 2)
@@ -425,7 +418,6 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 	constexpr uint32_t dhi = kSmemDescHiSw128;
 	const uint32_t df_issue = tmem + kColWorkF, db_issue = tmem + kColWorkB; // issuer's view of the two working accumulators
 	const uint32_t df_mine = tmem_addr(tmem, q * 32, kColWorkF + 32 * h), db_mine = tmem_addr(tmem, q * 32, kColWorkB + 32 * h);
-#if NRC_TRAIN_TS
 	const uint32_t af_issue = tmem + kColAF, ab_issue = tmem + kColAB;           // issuer's view of the two TMEM A operands
 	const uint32_t af_mine = tmem_addr(tmem, q * 32, kColAF + 16 * h), ab_mine = tmem_addr(tmem, q * 32, kColAB + 16 * h); // this thread's half row
 	// operand stored in TENSOR memory + accumulator drained -> one arrival per warp (no shared-memory traffic on this path)
@@ -436,14 +428,11 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 		if (lane == 0)
 			mbar_arrive(bar);
 	};
-#endif
 
 	// operand stored (generic-proxy smem writes fenced to the async proxy) + accumulator drained -> one arrival per warp
 	auto arrive_ready = [&](uint64_t *bar) {
 		fence_proxy_async_smem();
-#if NRC_TRAIN_TS
 		tc_wait_st();
-#endif
 		tc_fence_before();
 		__syncwarp();
 		if (lane == 0)
@@ -674,13 +663,11 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							tc_fence_after();
 							NRC_ITRACE(0x160 + k);
 							const uint32_t a_d = pool_desc + ring.fw[k] * (16384 >> 4), b_d = w_desc + (uint32_t)(k * (8192 >> 4));
-#if NRC_TRAIN_TS
 							if (k > 0) { // a_k from tensor memory (a_0 is in shared memory: SS form)
 #pragma unroll
 								for (int kk = 0; kk < 4; ++kk)
 									mma_ts_lh(df_issue, af_issue + kk * 8, b_d + kk * 2, dhi, k < 5 ? id_fwd64 : id_fwd16, kk > 0);
 							} else
-#endif
 							{
 #pragma unroll
 								for (int kk = 0; kk < 4; ++kk)
@@ -709,22 +696,16 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							const uint32_t acc = (r > 1) ? 1u : 0u; // dW accumulates from the CTA's second tile on
 							const uint32_t dw_acc = tmem_addr(tmem, dw_lane(l), dw_col(l)); // dW_l's accumulator
 							if (l == 5) {
-#if NRC_TRAIN_TS
 								mma_ts_lh(db_issue, ab_issue, wl, dhi, id_da, 0);
 								tc_commit(db_full);
 								mbar_wait(ds_ready, ds_ph); // delta_5 has reached shared memory too
 								ds_ph ^= 1;
 								tc_fence_after();
-#else
-								mma_ss_lh(db_issue, dl, wl, dhi, id_da, 0);
-								tc_commit(db_full);
-#endif
 #pragma unroll
 								for (int kk = 0; kk < 8; ++kk)
 									mma_ss_lh(dw_acc, al + kk * 128, dl + kk * 128, dhi, id_dw5t, acc | (kk > 0));
 							} else {
 								if (l > 0) {
-#if NRC_TRAIN_TS
 #pragma unroll
 									for (int kk = 0; kk < 4; ++kk)
 										mma_ts_lh(db_issue, ab_issue + kk * 8, wl + kk * 128, dhi, id_da, kk > 0);
@@ -734,12 +715,6 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 									ds_ph ^= 1;
 									tc_fence_after();
 									NRC_ITRACE(0x1A0 + l);
-#else
-#pragma unroll
-									for (int kk = 0; kk < 4; ++kk)
-										mma_ss_lh(db_issue, dl + kk * 2, wl + kk * 128, dhi, id_da, kk > 0);
-									tc_commit(db_full);
-#endif
 								}
 #pragma unroll
 								for (int kk = 0; kk < 8; ++kk)
@@ -871,7 +846,6 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 #pragma unroll
 							for (int i = 0; i < 16; ++i)
 								o[i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
-#if NRC_TRAIN_TS
 							tmem_st_x16(af_mine, o); // next layer's A operand: the forward chain only waits for this
 							arrive_tmem(af_ready);
 							NRC_GTRACE(0x20 + k);
@@ -883,11 +857,6 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							if (!(has_b && l >= 1))
 								fence_proxy_async_smem();
 							NRC_GTRACE(0x60 + k);
-#else
-							store_half_row(pool_sm + ring.fw[k + 1] * 16384, o);
-							NRC_GTRACE(0x20 + k);
-							arrive_ready(af_ready);
-#endif
 						} else { // output layer + loss gradient (NN_nv.glsl:148-196) -> delta_5
 							if (h == 0) {
 								uint32_t yv[4];
@@ -920,18 +889,14 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 									yo[0] = y[0], yo[1] = y[1], yo[2] = y[2];
 								}
 								uint8_t *rr = delta_sm + row * 128; // delta_5 (buffer 0): 16 fp16 = logical chunks 0 and 1 of the row
-#if NRC_TRAIN_TS
 								const uint32_t d5[8] = {cvt_pack_f16x2(g[0], g[1]), cvt_pack_f16x2(g[2], 0.0f), 0u, 0u, 0u, 0u, 0u, 0u};
 								tmem_st_x8(tmem_addr(tmem, q * 32, kColAB), d5); // K = 16: the backward stream's first A operand
-#endif
 								*(uint4 *)(rr + ((0 ^ (row & 7)) << 4)) = make_uint4(cvt_pack_f16x2(g[0], g[1]), cvt_pack_f16x2(g[2], 0.0f), 0u, 0u);
 								*(uint4 *)(rr + ((1 ^ (row & 7)) << 4)) = make_uint4(0u, 0u, 0u, 0u);
 							}
 							NRC_GTRACE(0x25);
 							arrive_ready(d5_ready); // delta_5 feeds backward layer 5 (step 0 of the next round)
-#if NRC_TRAIN_TS
 							arrive_ready(ds_ready); // (both copies are complete here: the loss epilogue is not on a per-layer chain)
-#endif
 						}
 					}
 					if (has_b && l >= 1) { // --------------------------------------------------- backward epilogue, layer l
@@ -957,7 +922,6 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							const __half2 dh = *(const __half2 *)&d2, ah = *(const __half2 *)&a[i];
 							o[i] = d2 & __hgt2_mask(ah, __float2half2_rn(0.0f)) & __heq2_mask(dh, dh);
 						}
-#if NRC_TRAIN_TS
 						if (l >= 2) { // delta_{l-1} feeds dA_{l-1} from tensor memory; the shared-memory copy (dW_{l-1}) follows off the chain
 							tmem_st_x16(ab_mine, o);
 							arrive_tmem(ab_ready);
@@ -970,11 +934,6 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							NRC_GTRACE(0x40 + l);
 							arrive_ready(ab_ready);
 						}
-#else
-						store_half_row(delta_sm + ((6 - l) & 1) * 16384, o);
-						NRC_GTRACE(0x40 + l);
-						arrive_ready(ab_ready);
-#endif
 						if (last_round && l <= 4) { // dW_{l+1} is final (its MMAs precede this step's commits): drain it now
 							if (l == 4) {
 								if (h == 0) {
