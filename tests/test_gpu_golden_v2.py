@@ -111,6 +111,12 @@ def test_standalone_encoder_is_the_fused_encoder(nrc, g2, dscene, n):
     a = nrc.encode_packed_inputs(packed, dscene)
     b = nrc.encode_inputs(nrc.unpack_inputs(packed, dscene))
     assert torch.equal(a, b)
+    # the same inputs inside 20-byte NRCEvalRecords (dst word in front, NRCRecord.glsl:11-14): stride 20, offset 4
+    ev = np.zeros((m, 5), np.uint32)
+    ev[:, 0] = 0xFFFFFFFF
+    ev[:, 1:] = g2["packed_inputs"][:m].view(np.uint32).reshape(m, 4)
+    d_ev = dev(ev.view(np.uint8).reshape(-1))
+    assert torch.equal(nrc.encode_packed_inputs(d_ev[4:], dscene, stride_bytes=20, n=m), a)
     st.close()
 
 
