@@ -847,11 +847,12 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 							for (int i = 0; i < 16; ++i)
 								o[i] = cvt_relu_pack_f16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
 							tmem_st_x16(af_mine, o); // next layer's A operand: the forward chain only waits for this
+							// the shared-memory copy (dW_{k+1}'s operand and the ReLU mask of the backward pass) is ISSUED under the latency of
+							// that TMEM store (the arrival below waits for the TMEM store only, not for these stores; their first reader is
+							// issued after later arrivals of this warp, which order them and their proxy fence): -2 .. 3 % on the 2^20 step
+							store_half_row(pool_sm + ring.fw[k + 1] * 16384, o);
 							arrive_tmem(af_ready);
 							NRC_GTRACE(0x20 + k);
-							// the shared-memory copy (dW_{k+1}'s operand and the ReLU mask of the backward pass) is off the chain: its first
-							// reader is issued after later arrivals of this warp, which order these stores and their proxy fence
-							store_half_row(pool_sm + ring.fw[k + 1] * 16384, o);
 							// (with a backward epilogue following in this step, its arrive_ready fences both copies: a fence of its own here
 							// made this warp sit out the drain of these stores before it could poll the backward accumulator's barrier)
 							if (!(has_b && l >= 1))
@@ -924,10 +925,13 @@ __global__ void __launch_bounds__(kTrainThreads, 1)
 						}
 						if (l >= 2) { // delta_{l-1} feeds dA_{l-1} from tensor memory; the shared-memory copy (dW_{l-1}) follows off the chain
 							tmem_st_x16(ab_mine, o);
+							store_half_row(delta_sm + ((6 - l) & 1) * 16384, o); // (issued under the TMEM store's latency, see the forward epilogue)
 							arrive_tmem(ab_ready);
 							NRC_GTRACE(0x40 + l);
-							store_half_row(delta_sm + ((6 - l) & 1) * 16384, o);
-							arrive_ready(ds_ready);
+							fence_proxy_async_smem(); // the copy (and the forward copy of this step) -> async proxy, then the second arrival
+							__syncwarp();
+							if (lane == 0)
+								mbar_arrive(ds_ready);
 							NRC_GTRACE(0x70 + l);
 						} else { // delta_0 only feeds dW_0
 							store_half_row(delta_sm + ((6 - l) & 1) * 16384, o);
