@@ -39,3 +39,30 @@ e1.record()
 torch.cuda.synchronize()
 t = e0.elapsed_time(e1) / 20 * 1e-3
 print(f"plain H2D of {n*20/1e6:.1f} MB: {t*1e6:.1f} us = {n*20/t/1e9:.1f} GB/s")
+# the same loop with an NVML sampler thread like bench.py's ClockSampler running beside it (5 ms period)
+import threading
+import pynvml
+pynvml.nvmlInit()
+hnd = pynvml.nvmlDeviceGetHandleByIndex(0)
+stop = threading.Event()
+def poll(period):
+    while not stop.is_set():
+        pynvml.nvmlDeviceGetClockInfo(hnd, pynvml.NVML_CLOCK_SM)
+        pynvml.nvmlDeviceGetCurrentClocksEventReasons(hnd)
+        time.sleep(period)
+for period in (0.005, 0.05):
+    stop.clear()
+    th = threading.Thread(target=poll, args=(period,), daemon=True)
+    th.start()
+    for rep in range(2):
+        for _ in range(12):
+            st.infer_eval_records_host(h_ev, scene, hout)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(20):
+            st.infer_eval_records_host(h_ev, scene, hout)
+        e1.record()
+        torch.cuda.synchronize()
+        print(f"with NVML sampler every {period*1e3:.0f} ms: e2e {e0.elapsed_time(e1)/20*1e3:7.1f} us/step")
+    stop.set()
+    th.join()
